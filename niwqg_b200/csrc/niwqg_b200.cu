@@ -1,0 +1,1054 @@
+// niwqg_b200.cu -- C-ABI host side of the B200-native niwqg hot path (see include/niwqg_b200.h).
+//
+// One handle owns every device buffer of one model instance and issues the whole
+// ETDRK4 step as a fixed sequence of kernel launches on one stream; nothing
+// crosses the ABI per transform.  No cuFFT, no CPU fallback: every arithmetic
+// kernel is in fft2d.cuh / kernels_family.cuh / kernels_qg.cuh.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "../../include/niwqg_b200.h"
+#include "fft2d.cuh"
+#include "kernels_family.cuh"
+#include "kernels_qg.cuh"
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char buf__[512];                                                                       \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            h->err = buf__;                                                                        \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+struct niwqg_handle {
+    niwqg_params p;
+    int N = 0, B = 1, model = 0, flags = 0;
+    bool qg = false;
+    int nk = 0;                 // spectral row length: N (c2c) or N/2+1 (QG)
+    size_t npts = 0, nspec = 0; // N*N, N*nk
+    double dk = 0, dx = 0, kappa2 = 0, hslash = 0, jscale = 1.0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> allocs;
+    std::string err;
+    long long launches = 0;
+    // tables
+    TableSet tq{}, tp{}, tc{};
+    double* filtr = nullptr;
+    cd* tw = nullptr;
+    // spectral state (c2c family: [B][N][N]; QG: [B][N][nk])
+    cd* qh[2] = {nullptr, nullptr};
+    cd* phih[2] = {nullptr, nullptr};
+    cd* chh[2] = {nullptr, nullptr};
+    int cq = 0, cp = 0, cc = 0;
+    cd *y1q = nullptr, *y1p = nullptr, *y1c = nullptr;
+    cd *F0q = nullptr, *F0p = nullptr, *F0c = nullptr, *Fabq = nullptr, *Fabp = nullptr, *Fabc = nullptr;
+    cd *ph = nullptr, *qwh = nullptr;
+    // physical carried fields
+    cd *phi = nullptr, *phix = nullptr, *phiy = nullptr, *lapphi = nullptr, *lap2phi = nullptr;
+    cd *uv = nullptr, *qs = nullptr, *uvq = nullptr;
+    // scratch
+    cd *W = nullptr, *P1 = nullptr, *P2 = nullptr;
+    double* rscratch = nullptr;   // [B][N][N] doubles
+    // reductions
+    double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *scal = nullptr, *stagev = nullptr;
+    bool q_set = false, phi_set = false;
+};
+
+// ---------------------------------------------------------------------------
+static int dalloc(niwqg_handle* h, void** p, size_t bytes, bool zero = true) {
+    CK(cudaMalloc(p, bytes));
+    h->allocs.push_back(*p);
+    if (zero) CK(cudaMemsetAsync(*p, 0, bytes, h->stream));
+    return 0;
+}
+#define DA(ptr, bytes)                                              \
+    do {                                                            \
+        int r__ = dalloc(h, (void**)&(ptr), (bytes));               \
+        if (r__) return r__;                                        \
+    } while (0)
+
+static dim3 pw_grid(const niwqg_handle* h) { return dim3(NIWQG_PW_BLOCKS, h->B); }
+
+static void build_twiddles(int N, std::vector<cd>& tw) {
+    tw.assign(fftc::tw_table_len(N) + 1, make_double2(1.0, 0.0));
+    const long double PI = 3.141592653589793238462643383279502884L;
+    for (int NS = 16; NS < N; NS *= 16) {
+        const int R = (N / NS >= 16) ? 16 : N / NS;
+        for (int kk = 0; kk < NS; ++kk) {
+            const long double a = -2.0L * PI * (long double)kk / ((long double)NS * R);
+            tw[fftc::tw_offset(NS) + kk] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+    }
+}
+
+// 2-D c2c transform of `batch` members: in -> out (may alias), forward or inverse
+static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro, int batch, int epi = EPI_NONE,
+                void* real_out = nullptr) {
+    FftArgs a{};
+    a.tw = h->tw;
+    a.dk = h->dk;
+    // pass 1: rows
+    a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE;
+    a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0;
+    CK(launch_pass<false>(h->N, a, batch, h->stream));
+    // pass 2: columns
+    a.in = out; a.out = (epi == EPI_REAL_OUT) ? real_out : (void*)out; a.pro = PRO_NONE; a.epi = epi;
+    a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
+    a.scale = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
+    CK(launch_pass<true>(h->N, a, batch, h->stream));
+    h->launches += 2;
+    return 0;
+}
+#define FFT(...)                          \
+    do {                                  \
+        int r__ = fft2(h, __VA_ARGS__);   \
+        if (r__) return r__;              \
+    } while (0)
+
+static int finalize(niwqg_handle* h, int K, double* out, int is_max = 0) {
+    k_finalize<<<h->B, 32, 0, h->stream>>>(h->part, NIWQG_PW_BLOCKS, K, out, is_max);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+#define FIN(...)                              \
+    do {                                      \
+        int r__ = finalize(h, __VA_ARGS__);   \
+        if (r__) return r__;                  \
+    } while (0)
+
+__global__ void k_budget(BudgetArgs a) {
+    const int m = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const double* sd = a.sumsD + (size_t)m * SD_COUNT;
+    const double* se = a.sumsE + (size_t)m * SE_COUNT;
+    double* sc = a.scal + (size_t)m * NIWQG_S_COUNT;
+    const double M = a.M;
+    const double g1 = 0.5 * 0.5 * a.hslash * (sd[SD_G1] / M) / a.f;
+    const double g2 = 0.5 * a.hslash * (sd[SD_G2] / M) / a.f;
+    const double x1 = (sd[SD_X1] / M) / a.f, x2 = (sd[SD_X2] / M) / a.f;
+    const double ar = sd[SD_PHI_R] / M, ai = sd[SD_PHI_I] / M, br = sd[SD_QPC_R] / M, bi = sd[SD_QPC_I] / M;
+    const double pi = 0.5 * (ar * bi + ai * br);
+    const double M2 = M * M;
+    const double ep_psi = a.nu4 * (se[SE_QLAP2PSI] / M2) - a.nu * (se[SE_PLAPQ] / M2) + a.mu * (se[SE_PQ] / M2);
+    const double chi_phi = -0.5 * a.nu4w * (se[SE_WV6PHI] / M2) / a.kappa2 - 0.5 * a.nuw * (sd[SD_LAP2] / M) / a.kappa2 -
+                           0.5 * a.muw * (sd[SD_GRAD2] / M) / a.kappa2;
+    const double ep_phi = -a.nu4w * (sd[SD_LAP2] / M) - a.nuw * (sd[SD_GRAD2] / M) - a.muw * (sd[SD_PHI2] / M);
+    sc[NIWQG_S_GAMMA1] = g1; sc[NIWQG_S_GAMMA2] = g2; sc[NIWQG_S_XI1] = x1; sc[NIWQG_S_XI2] = x2; sc[NIWQG_S_PI] = pi;
+    if (a.stage == 0) {
+        sc[NIWQG_S_EP_PSI] = ep_psi; sc[NIWQG_S_CHI_PHI] = chi_phi; sc[NIWQG_S_EP_PHI] = ep_phi;
+        return;
+    }
+    double* sv = a.stagev + (size_t)m * 12 + (a.stage - 1) * 3;
+    sv[0] = -(g1 + g2) + (x1 + x2) + ep_psi;
+    sv[1] = g1 + g2 + chi_phi;
+    sv[2] = ep_phi;
+    if (a.stage == 4) {
+        const double* s0 = a.stagev + (size_t)m * 12;
+        sc[NIWQG_S_KE] += a.dt * (s0[0] + 2 * (s0[3] + s0[6]) + s0[9]) / 6.;
+        sc[NIWQG_S_PW] += a.dt * (s0[1] + 2 * (s0[4] + s0[7]) + s0[10]) / 6.;
+        sc[NIWQG_S_KW] += a.dt * (s0[2] + 2 * (s0[5] + s0[8]) + s0[11]) / 6.;
+    }
+}
+
+static BudgetArgs budget_args(niwqg_handle* h, int stage) {
+    BudgetArgs b{};
+    b.stage = stage; b.M = (double)h->npts; b.f = h->p.f; b.hslash = h->hslash; b.kappa2 = h->kappa2; b.dt = h->p.dt;
+    b.nu4 = h->p.nu4; b.nu = h->p.nu; b.mu = h->p.mu; b.nu4w = h->p.nu4w; b.nuw = h->p.nuw; b.muw = h->p.muw;
+    b.sumsD = h->sumsD; b.sumsE = h->sumsE; b.scal = h->scal; b.stagev = h->stagev;
+    return b;
+}
+
+// ---------------------------------------------------------------------------
+// family building blocks
+// ---------------------------------------------------------------------------
+// phi-derived physical fields from the current phih: phi, lapphi (+lap2phi) always; phix, phiy when `grad`
+static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
+    const cd* ph = h->phih[h->cp];
+    if (want_phi) FFT(ph, h->phi, true, PRO_NONE, h->B);
+    if (grad) {
+        FFT(ph, h->phix, true, PRO_IK, h->B);
+        FFT(ph, h->phiy, true, PRO_IL, h->B);
+    }
+    if (lap) {
+        FFT(ph, h->lapphi, true, PRO_NEG_WV2, h->B);
+        if (h->flags & MF_HAS_LAP2) FFT(ph, h->lap2phi, true, PRO_WV4, h->B);
+    }
+    return 0;
+}
+
+// _invert + _calc_rel_vorticity + (u,v) for the current (qh, phi, phix, phiy)
+static int invert_family(niwqg_handle* h) {
+    InvertArgs ia{};
+    ia.g = Grid{h->N, h->dk};
+    ia.flags = h->flags; ia.f = h->p.f; ia.qh = h->qh[h->cq]; ia.filtr = h->filtr;
+    ia.ph = h->ph; ia.qs = h->qs;
+    if (h->flags & MF_WAVE_PV) {
+        k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale);
+        CK(cudaGetLastError());
+        h->launches++;
+        FFT(h->W, h->W, false, PRO_NONE, h->B);
+        ia.W = h->W; ia.qwh = h->qwh; ia.inv_jscale = 1.0 / h->jscale;
+    }
+    if (h->flags & MF_YBJ) ia.uvgen = h->uv;
+    k_spec_invert<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ia);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (h->flags & MF_YBJ) {
+        FFT(h->uv, h->uv, true, PRO_NONE, h->B);
+    } else {
+        FFT(h->ph, h->uv, true, PRO_UV, h->B);
+        FFT(h->qs, h->qs, true, PRO_NONE, h->B);
+    }
+    return 0;
+}
+
+static PhysArgs phys_args(niwqg_handle* h, int extra_flags) {
+    PhysArgs pa{};
+    pa.npts = h->npts; pa.flags = h->flags | extra_flags;
+    pa.nu4w = h->p.nu4w; pa.nuw = h->p.nuw; pa.muw = h->p.muw;
+    pa.uv = h->uv; pa.qs = h->qs; pa.phi = h->phi; pa.phix = h->phix; pa.phiy = h->phiy;
+    pa.lapphi = h->lapphi; pa.lap2phi = h->lap2phi; pa.uvq = h->uvq;
+    pa.P1 = h->P1; pa.P2 = h->P2; pa.partials = h->part;
+    return pa;
+}
+
+static int ql_wave_velocity(niwqg_handle* h) {   // uq, vq from the current qh (QLModel.py:65-66)
+    k_spec_uvq<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(Grid{h->N, h->dk}, h->qh[h->cq], h->uvq);
+    CK(cudaGetLastError());
+    h->launches++;
+    FFT(h->uvq, h->uvq, true, PRO_NONE, h->B);
+    return 0;
+}
+
+static int step_family(niwqg_handle* h) {
+    const bool ybj = (h->flags & MF_YBJ) != 0, ql = (h->flags & MF_QL_ADV) != 0;
+    const int oq = h->cq, op = h->cp;          // y0 buffers
+    const int nq = ybj ? oq : 1 - oq, np = 1 - op;
+    for (int st = 1; st <= 4; ++st) {
+        if (ybj) {   // _calc_grad_phi from the stage's phih (YBJModel.py:135-139); phi stays stale (F7)
+            const cd* cur = (st == 1) ? h->phih[op] : h->phih[np];
+            FFT(cur, h->phix, true, PRO_IK, h->B);
+            FFT(cur, h->phiy, true, PRO_IL, h->B);
+        }
+        StageArgs sa{};
+        sa.g = Grid{h->N, h->dk};
+        sa.stage = st; sa.flags = h->flags; sa.do_q = ybj ? 0 : 1; sa.do_phi = 1;
+        sa.P1 = h->P1; sa.P2 = h->P2;
+        sa.y0q = h->qh[oq]; sa.y0p = h->phih[op]; sa.yq = h->qh[nq]; sa.yp = h->phih[np];
+        sa.y1q = h->y1q; sa.y1p = h->y1p; sa.F0q = h->F0q; sa.F0p = h->F0p; sa.Fabq = h->Fabq; sa.Fabp = h->Fabp;
+        sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
+        if (!ql) {
+            PhysArgs pa = phys_args(h, 0);
+            k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+            CK(cudaGetLastError());
+            h->launches++;
+            if (!ybj) {
+                FIN(SD_COUNT, h->sumsD);
+                FFT(h->P1, h->P1, false, PRO_NONE, h->B);
+            }
+            FFT(h->P2, h->P2, false, PRO_NONE, h->B);
+            k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+            CK(cudaGetLastError());
+            h->launches++;
+            if (st == 1) { h->cq = nq; h->cp = np; }
+        } else {
+            // repaired QL: jacobian_psi_phi reads qh AFTER the stage's q update (Kernel.py:326-332 order),
+            // so the stage is split: q half, wave velocity from the new qh, phi half.
+            PhysArgs pa = phys_args(h, MF_SKIP_P2);
+            k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+            CK(cudaGetLastError());
+            FIN(SD_COUNT, h->sumsD);
+            FFT(h->P1, h->P1, false, PRO_NONE, h->B);
+            sa.do_phi = 0;
+            k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+            CK(cudaGetLastError());
+            if (st == 1) h->cq = nq;
+            int r = ql_wave_velocity(h);
+            if (r) return r;
+            pa = phys_args(h, MF_SKIP_P1);
+            k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+            CK(cudaGetLastError());
+            FFT(h->P2, h->P2, false, PRO_NONE, h->B);
+            sa.do_q = 0; sa.do_phi = 1;
+            k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+            CK(cudaGetLastError());
+            h->launches += 4;
+            if (st == 1) h->cp = np;
+        }
+        if (!ybj) {
+            FIN(SE_COUNT, h->sumsE);
+            k_budget<<<h->B, 32, 0, h->stream>>>(budget_args(h, st));
+            CK(cudaGetLastError());
+            h->launches++;
+            // self.phi = ifft(phih); _invert(); _calc_rel_vorticity()  (Kernel.py:337-339 / :395-397)
+            const bool grad = (h->flags & MF_WAVE_PV) != 0;   // only jacobian_phic_phi refreshes phix, phiy (F6)
+            int r = wave_fields(h, true, grad, true);
+            if (r) return r;
+            r = invert_family(h);
+            if (r) return r;
+        }
+    }
+    if (ybj) FFT(h->phih[h->cp], h->phi, true, PRO_NONE, h->B);   // YBJModel.py:87
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// QG model (half spectrum)  -- see kernels_qg.cuh
+// ---------------------------------------------------------------------------
+static int qg_expand_and_invert(niwqg_handle* h, const cd* qh_cur, bool want_uv = true) {
+    QgExpandArgs ea{};
+    ea.N = h->N; ea.nk = h->nk; ea.dk = h->dk; ea.qh = qh_cur; ea.ph = h->ph; ea.uv = want_uv ? h->uv : nullptr; ea.qs = h->qs;
+    k_qg_expand<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (want_uv) FFT(h->uv, h->uv, true, PRO_NONE, h->B);
+    FFT(h->qs, h->qs, true, PRO_NONE, h->B);
+    return 0;
+}
+
+static int qg_scalar_physical(niwqg_handle* h, const cd* ch_cur) {
+    QgExpand1Args ea{};
+    ea.N = h->N; ea.nk = h->nk; ea.dk = h->dk; ea.in = ch_cur; ea.out = h->W; ea.mode = QGX_PLAIN;
+    k_qg_expand1<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+    CK(cudaGetLastError());
+    h->launches++;
+    FFT(h->W, h->W, true, PRO_NONE, h->B);
+    return 0;
+}
+
+static int step_qg(niwqg_handle* h) {
+    const bool ps = h->p.passive_scalar != 0;
+    const int oq = h->cq, nq = 1 - oq, oc = h->cc, nc = 1 - oc;
+    for (int st = 1; st <= 4; ++st) {
+        // jacobian_psi_q (QGModel.py:469-481): u, v, q from the current (qh, ph)
+        const cd* cur = (st == 1) ? h->qh[oq] : h->qh[nq];
+        int r = qg_expand_and_invert(h, cur);
+        if (r) return r;
+        const cd* ccur = nullptr;
+        if (ps) {
+            ccur = (st == 1) ? h->chh[oc] : h->chh[nc];
+            r = qg_scalar_physical(h, ccur);       // c = irfft2(ch) -> W.x   (QGModel.py:493)
+            if (r) return r;
+        }
+        k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, ps ? h->W : nullptr, h->P1, h->P2,
+                                                                       h->npts);
+        CK(cudaGetLastError());
+        h->launches++;
+        FFT(h->P1, h->P1, false, PRO_NONE, h->B);
+        if (ps) FFT(h->P2, h->P2, false, PRO_NONE, h->B);
+        QgStageArgs sa{};
+        sa.N = h->N; sa.nk = h->nk; sa.dk = h->dk; sa.stage = st; sa.ps = ps ? 1 : 0;
+        sa.P1 = h->P1; sa.P2 = h->P2;
+        sa.y0q = h->qh[oq]; sa.yq = h->qh[nq]; sa.y1q = h->y1q; sa.F0q = h->F0q; sa.Fabq = h->Fabq;
+        sa.y0c = h->chh[oc]; sa.yc = h->chh[nc]; sa.y1c = h->y1c; sa.F0c = h->F0c; sa.Fabc = h->Fabc;
+        sa.tq = h->tq; sa.tc = h->tc; sa.filtr = h->filtr; sa.partials = h->part;
+        sa.nu4c = h->p.nu4c;
+        k_qg_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+        CK(cudaGetLastError());
+        h->launches++;
+        if (st == 1) { h->cq = nq; h->cc = nc; }
+        FIN(QE_COUNT, h->sumsE);
+        QgBudgetArgs ba{};
+        ba.stage = st; ba.M = (double)h->npts; ba.dt = h->p.dt; ba.nu4 = h->p.nu4; ba.nu = h->p.nu; ba.mu = h->p.mu;
+        ba.nu4c = h->p.nu4c; ba.muc = h->p.muc; ba.ps = ps ? 1 : 0;
+        ba.sumsE = h->sumsE; ba.scal = h->scal; ba.stagev = h->stagev;
+        k_qg_budget<<<h->B, 32, 0, h->stream>>>(ba);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    // final _invert + physical q (and c) (QGModel.py:397-404); u, v stay those of the stage-4 Jacobian,
+    // which is what Gamma_c reads at the diagnostics tick (QGModel.py:731 -> :494)
+    int r = qg_expand_and_invert(h, h->qh[h->cq], false);
+    if (r) return r;
+    if (ps) { r = qg_scalar_physical(h, h->chh[h->cc]); if (r) return r; }
+    return 0;
+}
+
+// Gamma_c sum (QGModel.py:731): sum FH(lapc-hat) conj(FH(jacobian_psi_c-hat)) -> sumsD[member]
+static int qg_gamma_c(niwqg_handle* h) {
+    int r = qg_scalar_physical(h, h->chh[h->cc]);      // jacobian_psi_c refreshes c = irfft2(ch) (QGModel.py:493)
+    if (r) return r;
+    k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, h->W, h->P1, h->P2, h->npts);
+    CK(cudaGetLastError());
+    FFT(h->P2, h->P2, false, PRO_NONE, h->B);
+    k_qg_gamma_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->P2, h->chh[h->cc], h->N, h->nk, h->dk, h->part);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    FIN(1, h->sumsD);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* niwqg_last_error(const niwqg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int niwqg_destroy(niwqg_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+static int create_impl(niwqg_handle* h) {
+    const niwqg_params& p = h->p;
+    const int N = p.nx;
+    CK(cudaSetDevice(p.device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    h->N = N; h->B = p.batch; h->model = p.model; h->qg = (p.model == NIWQG_MODEL_QG);
+    h->nk = h->qg ? N / 2 + 1 : N;
+    h->npts = (size_t)N * N; h->nspec = (size_t)N * h->nk;
+    h->dk = 2.0 * M_PI / p.L; h->dx = p.L / N;
+    {   // power of two nearest 1/k_mid^2, k_mid = dk*N/8 (scaling of the packed wave-PV transform)
+        const double kmid = h->dk * N / 8.0;
+        h->jscale = exp2(rint(log2(1.0 / (kmid * kmid))));
+    }
+    if (!h->qg) {
+        const double kappa = p.m * p.f / p.N;     // Kernel.py:121-125
+        h->kappa2 = kappa * kappa;
+        h->hslash = p.f / h->kappa2;
+    }
+    switch (p.model) {
+        case NIWQG_MODEL_COUPLED: h->flags = MF_WAVE_PV | MF_FIX00; break;
+        case NIWQG_MODEL_UNCOUPLED: h->flags = MF_FIX00; break;
+        case NIWQG_MODEL_YBJ: h->flags = MF_YBJ; break;
+        case NIWQG_MODEL_QL: h->flags = MF_WAVE_PV | MF_QL_ADV; break;
+        default: h->flags = 0;
+    }
+    if (!h->qg && p.nu4w != 0.0) h->flags |= MF_HAS_LAP2;
+    const size_t B = h->B, cb = sizeof(cd);
+    const size_t fsz = B * h->npts * cb, ssz = B * h->nspec * cb, tsz = h->nspec * cb;
+    // twiddles
+    std::vector<cd> tw;
+    build_twiddles(N, tw);
+    DA(h->tw, tw.size() * cb);
+    CK(cudaMemcpyAsync(h->tw, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    // tables
+    auto alloc_tables = [&](TableSet& t) -> int {
+        DA(t.E, tsz); DA(t.E2, tsz); DA(t.Q, tsz); DA(t.f0, tsz); DA(t.fab, tsz); DA(t.fc, tsz);
+        return 0;
+    };
+    DA(h->filtr, h->nspec * sizeof(double));
+    InitArgs ia{};
+    ia.N = N; ia.nk = h->nk; ia.half = h->qg ? 1 : 0; ia.dk = h->dk; ia.dt = p.dt; ia.dx = h->dx; ia.U = p.U;
+    ia.use_filter = p.use_filter; ia.dealias = p.dealias;
+    bool filtr_done = false;
+    if (p.model != NIWQG_MODEL_YBJ) {
+        if (alloc_tables(h->tq)) return -2;
+        ia.re_a4 = p.nu4; ia.re_a2 = p.nu; ia.re_a0 = p.mu; ia.im_wv2 = 0.0; ia.beta = h->qg ? p.beta : 0.0;
+        ia.t = h->tq; ia.filtr = h->filtr; filtr_done = true;
+        k_init_tables<<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(ia);
+        CK(cudaGetLastError());
+    }
+    if (!h->qg) {
+        if (alloc_tables(h->tp)) return -2;
+        ia.re_a4 = p.nu4w; ia.re_a2 = p.nuw; ia.re_a0 = p.muw; ia.im_wv2 = 0.5 * p.f / h->kappa2; ia.beta = 0.0;
+        ia.t = h->tp; ia.filtr = filtr_done ? nullptr : h->filtr;
+        k_init_tables<<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(ia);
+        CK(cudaGetLastError());
+    } else if (p.passive_scalar) {
+        if (alloc_tables(h->tc)) return -2;
+        ia.re_a4 = p.nu4c; ia.re_a2 = p.nuc; ia.re_a0 = p.muc; ia.im_wv2 = 0.0; ia.beta = 0.0; ia.U = 0.0;   // QGModel.py:452
+        ia.t = h->tc; ia.filtr = nullptr;
+        k_init_tables<<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(ia);
+        CK(cudaGetLastError());
+    }
+    // state
+    DA(h->qh[0], ssz); DA(h->ph, ssz); DA(h->uv, fsz); DA(h->qs, fsz);
+    DA(h->P1, fsz); DA(h->P2, fsz); DA(h->W, fsz);
+    DA(h->rscratch, B * h->npts * sizeof(double));
+    if (p.model != NIWQG_MODEL_YBJ) { DA(h->qh[1], ssz); DA(h->y1q, ssz); DA(h->F0q, ssz); DA(h->Fabq, ssz); }
+    if (!h->qg) {
+        DA(h->phih[0], ssz); DA(h->phih[1], ssz); DA(h->y1p, ssz); DA(h->F0p, ssz); DA(h->Fabp, ssz);
+        DA(h->phi, fsz); DA(h->phix, fsz); DA(h->phiy, fsz); DA(h->lapphi, fsz);
+        if (h->flags & MF_HAS_LAP2) DA(h->lap2phi, fsz);
+        if (h->flags & MF_WAVE_PV) DA(h->qwh, ssz);
+        if (h->flags & MF_QL_ADV) DA(h->uvq, fsz);
+    } else if (p.passive_scalar) {
+        DA(h->chh[0], ssz); DA(h->chh[1], ssz); DA(h->y1c, ssz); DA(h->F0c, ssz); DA(h->Fabc, ssz);
+    }
+    DA(h->part, B * NIWQG_PW_BLOCKS * 16 * sizeof(double));
+    DA(h->sumsD, B * 16 * sizeof(double)); DA(h->sumsE, B * 16 * sizeof(double)); DA(h->sumsX, B * 16 * sizeof(double));
+    DA(h->scal, B * NIWQG_S_COUNT * sizeof(double)); DA(h->stagev, B * 24 * sizeof(double));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int niwqg_create(const niwqg_params* p, niwqg_handle** out) {
+    if (!p || !out) { g_create_error = "null argument"; return -1; }
+    *out = nullptr;
+    const int N = p->nx;
+    if (N < 32 || N > 8192 || (N & (N - 1))) { g_create_error = "nx must be a power of two in [32, 8192]"; return -1; }
+    if (p->batch < 1) { g_create_error = "batch must be >= 1"; return -1; }
+    if (p->model < NIWQG_MODEL_QG || p->model > NIWQG_MODEL_QL) { g_create_error = "unknown model"; return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device: niwqg_b200 has no CPU fallback";
+        return -3;
+    }
+    niwqg_handle* h = new niwqg_handle();
+    h->p = *p;
+    int r = create_impl(h);
+    if (r) { g_create_error = h->err; niwqg_destroy(h); return r; }
+    *out = h;
+    return 0;
+}
+
+int niwqg_sync(niwqg_handle* h) {
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+long long niwqg_launch_count(const niwqg_handle* h) { return h->launches; }
+void* niwqg_stream(const niwqg_handle* h) { return (void*)h->stream; }
+
+static int ke_qg_family(niwqg_handle* h) {   // 0.5*spec_var(wv*ph) (Kernel.py:600-602) -> sumsX via k_spec_sums
+    SpecSumArgs sa{};
+    sa.g = Grid{h->N, h->dk}; sa.ph = h->ph; sa.qh = h->qh[h->cq]; sa.qwh = h->qwh;
+    sa.phih = (h->flags & MF_HAS_LAP2) ? h->phih[h->cp] : nullptr;
+    k_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
+    CK(cudaGetLastError());
+    h->launches++;
+    FIN(SS_COUNT, h->sumsX);
+    return 0;
+}
+
+__global__ void k_set_scalar_from_sum(double* scal, int slot, const double* sums, int K, int idx, double factor) {
+    const int m = blockIdx.x;
+    if (threadIdx.x == 0) scal[(size_t)m * NIWQG_S_COUNT + slot] = factor * sums[(size_t)m * K + idx];
+}
+
+int niwqg_set_q(niwqg_handle* h, const double* q, int on_device) {
+    CK(cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->B * h->npts;
+    CK(cudaMemcpyAsync(h->rscratch, q, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       h->stream));
+    const double M2 = (double)h->npts * (double)h->npts;
+    if (h->qg) {
+        // qh = rfft2(q): full c2c of the real field, keep columns 0..N/2 (QGModel.py:516-518)
+        FFT(h->rscratch, h->W, false, PRO_REAL_IN, h->B);
+        k_qg_take_half<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->W, h->qh[h->cq], h->N, h->nk);
+        CK(cudaGetLastError());
+        h->launches++;
+        int r = qg_expand_and_invert(h, h->qh[h->cq]);
+        if (r) return r;
+        // physical q carried for ep_psi (stale-q semantics) is the user's array: qs.x <- q
+        k_qg_set_q_real<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->rscratch, h->qs, h->npts);
+        CK(cudaGetLastError());
+        h->launches++;
+        QgSumArgs sa{};
+        sa.N = h->N; sa.nk = h->nk; sa.dk = h->dk; sa.qh = h->qh[h->cq]; sa.ch = nullptr;
+        k_qg_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
+        CK(cudaGetLastError());
+        h->launches++;
+        FIN(QS_COUNT, h->sumsX);
+        k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_KE, h->sumsX, QS_COUNT, QS_KE, 0.5 / M2);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        h->q_set = true;
+        return 0;
+    }
+    FFT(h->rscratch, h->qh[h->cq], false, PRO_REAL_IN, h->B);
+    if (h->flags & MF_WAVE_PV) {   // jacobian_phic_phi refreshes phix, phiy from the current phih (CoupledModel.py:70)
+        int r = wave_fields(h, false, true, false);
+        if (r) return r;
+    }
+    int r = invert_family(h);
+    if (r) return r;
+    if (h->flags & MF_YBJ) {
+        // YBJ._invert does not touch q: q (and q_psi) stay the user's array (YBJModel.py:141-146, Kernel.py:530)
+        k_real_to_cplx<<<pw_grid(h).x, NIWQG_PW_THREADS, 0, h->stream>>>(h->rscratch, h->qs, n);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    r = ke_qg_family(h);
+    if (r) return r;
+    k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_KE, h->sumsX, SS_COUNT, SS_KE, 0.5 / M2);
+    CK(cudaGetLastError());
+    h->launches++;
+    h->q_set = true;
+    return 0;
+}
+
+static int pe_niw_refresh(niwqg_handle* h, double* sums_out) {   // Kernel.py:608-611
+    int r = wave_fields(h, false, true, false);
+    if (r) return r;
+    k_grad2_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phix, h->phiy, h->npts, h->part);
+    CK(cudaGetLastError());
+    h->launches++;
+    FIN(1, sums_out);
+    return 0;
+}
+
+__global__ void k_phi2_sum(const cd* __restrict__ phi, size_t npts, double* partials) {
+    const size_t mb = (size_t)blockIdx.y * npts;
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += (size_t)gridDim.x * blockDim.x) {
+        const cd p = phi[mb + i];
+        s[0] += p.x * p.x + p.y * p.y;
+    }
+    block_reduce_store<1>(s, partials);
+}
+
+int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
+    if (h->qg) { h->err = "set_phi: QGModel has no wave field"; return -1; }
+    CK(cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->B * h->npts;
+    CK(cudaMemcpyAsync(h->phi, phi, n * sizeof(cd), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       h->stream));
+    FFT(h->phi, h->phih[h->cp], false, PRO_NONE, h->B);
+    int r = pe_niw_refresh(h, h->sumsX);
+    if (r) return r;
+    const double M = (double)h->npts;
+    k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_PW, h->sumsX, 1, 0, 0.25 / M / h->kappa2);
+    CK(cudaGetLastError());
+    k_phi2_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->npts, h->part);
+    CK(cudaGetLastError());
+    FIN(1, h->sumsX);
+    k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_KW, h->sumsX, 1, 0, 0.5 / M);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    // lapphi follows phih (the reference recomputes it at every _calc_energy_conversion, Kernel.py:685)
+    r = wave_fields(h, false, false, true);
+    if (r) return r;
+    h->phi_set = true;
+    return 0;
+}
+
+int niwqg_set_c(niwqg_handle* h, const double* c, int on_device) {
+    if (!h->qg || !h->p.passive_scalar) { h->err = "set_c: needs QGModel(passive_scalar=True)"; return -1; }
+    CK(cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->B * h->npts;
+    CK(cudaMemcpyAsync(h->rscratch, c, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       h->stream));
+    FFT(h->rscratch, h->W, false, PRO_REAL_IN, h->B);
+    k_qg_take_half<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->W, h->chh[h->cc], h->N, h->nk);
+    CK(cudaGetLastError());
+    QgSumArgs sa{};
+    sa.N = h->N; sa.nk = h->nk; sa.dk = h->dk; sa.qh = h->qh[h->cq]; sa.ch = h->chh[h->cc];
+    k_qg_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
+    CK(cudaGetLastError());
+    FIN(QS_COUNT, h->sumsX);
+    const double M2 = (double)h->npts * (double)h->npts;
+    k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_CVAR, h->sumsX, QS_COUNT, QS_C2, 1.0 / M2);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    // physical c carried in W.x is the user's array
+    k_real_to_cplx<<<pw_grid(h).x, NIWQG_PW_THREADS, 0, h->stream>>>(h->rscratch, h->W, n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int niwqg_step(niwqg_handle* h, int nsteps) {
+    CK(cudaSetDevice(h->p.device));
+    if (!h->q_set || (!h->qg && !h->phi_set)) {
+        // the reference raises AttributeError (u, v, phix... undefined) when stepping an unseeded model
+        h->err = "step: set_q" + std::string(h->qg ? "" : " and set_phi") + " must be called first";
+        return -1;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        int r = h->qg ? step_qg(h) : step_family(h);
+        if (r) return r;
+    }
+    return 0;
+}
+
+int niwqg_time_steps(niwqg_handle* h, int nsteps, float* ms) {
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int r = niwqg_step(h, nsteps);
+    if (r) return r;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+
+int niwqg_get_scalars(niwqg_handle* h, double* out) {
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaMemcpyAsync(out, h->scal, (size_t)h->B * NIWQG_S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int niwqg_status(niwqg_handle* h, double* out) {
+    CK(cudaSetDevice(h->p.device));
+    std::vector<double> sx((size_t)h->B * 16), tmp((size_t)h->B * 16);
+    const double M = (double)h->npts, M2 = M * M;
+    if (h->qg) {
+        // ke_qg and cfl from the current (qh, ph): u, v are refreshed from ph (QGModel.py:571-629)
+        int r = qg_expand_and_invert(h, h->qh[h->cq]);
+        if (r) return r;
+        QgSumArgs sa{};
+        sa.N = h->N; sa.nk = h->nk; sa.dk = h->dk; sa.qh = h->qh[h->cq]; sa.ch = nullptr;
+        k_qg_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
+        CK(cudaGetLastError());
+        FIN(QS_COUNT, h->sumsX);
+        CK(cudaMemcpyAsync(sx.data(), h->sumsX, (size_t)h->B * QS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        k_cfl_max<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, nullptr, h->npts, h->part);
+        CK(cudaGetLastError());
+        FIN(1, h->sumsD, 1);
+        CK(cudaMemcpyAsync(tmp.data(), h->sumsD, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->launches += 2;
+        for (int m = 0; m < h->B; ++m) {
+            out[m * 4 + 0] = 0.5 * sx[(size_t)m * QS_COUNT + QS_KE] / M2;
+            out[m * 4 + 1] = 0.0; out[m * 4 + 2] = 0.0;
+            out[m * 4 + 3] = tmp[m] * h->p.dt / h->dx;
+        }
+        return 0;
+    }
+    int r = ke_qg_family(h);
+    if (r) return r;
+    CK(cudaMemcpyAsync(sx.data(), h->sumsX, (size_t)h->B * SS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < h->B; ++m) out[m * 4 + 0] = 0.5 * sx[(size_t)m * SS_COUNT + SS_KE] / M2;
+    k_phi2_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->npts, h->part);
+    CK(cudaGetLastError());
+    FIN(1, h->sumsX);
+    CK(cudaMemcpyAsync(tmp.data(), h->sumsX, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < h->B; ++m) out[m * 4 + 1] = 0.5 * tmp[m] / M;
+    r = pe_niw_refresh(h, h->sumsX);
+    if (r) return r;
+    CK(cudaMemcpyAsync(tmp.data(), h->sumsX, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < h->B; ++m) out[m * 4 + 2] = 0.25 * tmp[m] / M / h->kappa2;
+    k_cfl_max<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->phi, h->npts, h->part);
+    CK(cudaGetLastError());
+    FIN(1, h->sumsX, 1);
+    CK(cudaMemcpyAsync(tmp.data(), h->sumsX, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->launches += 2;
+    for (int m = 0; m < h->B; ++m) out[m * 4 + 3] = tmp[m] * h->p.dt / h->dx;
+    return 0;
+}
+
+int niwqg_diagnostics(niwqg_handle* h, double* out) {
+    CK(cudaSetDevice(h->p.device));
+    const int B = h->B;
+    const double M = (double)h->npts, M2 = M * M;
+    std::vector<double> sc((size_t)B * NIWQG_S_COUNT), sd((size_t)B * 16), ss((size_t)B * 16), sg((size_t)B), s3((size_t)B * 3),
+        sq((size_t)B);
+    if (h->qg) {
+        // _calc_derived_fields + registry of QGModel.py:632-737
+        const bool ps = h->p.passive_scalar != 0;
+        QgSumArgs sa{};
+        sa.N = h->N; sa.nk = h->nk; sa.dk = h->dk; sa.qh = h->qh[h->cq]; sa.ch = ps ? h->chh[h->cc] : nullptr;
+        sa.qs = h->qs;
+        k_qg_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
+        CK(cudaGetLastError());
+        FIN(QS_COUNT, h->sumsX);
+        k_qg_q2_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->qs, h->npts, h->part);
+        CK(cudaGetLastError());
+        FIN(1, h->sumsD);
+        h->launches += 2;
+        CK(cudaMemcpyAsync(ss.data(), h->sumsX, (size_t)B * QS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(sq.data(), h->sumsD, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(sc.data(), h->scal, sc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        double gam[64] = {0};
+        if (ps) {
+            // Gamma_c = 2*mean(lapc * irfft2(jacobian_psi_c))  (QGModel.py:731)
+            int r = qg_gamma_c(h);
+            if (r) return r;
+            CK(cudaMemcpyAsync(sg.data(), h->sumsD, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (int m = 0; m < B && m < 64; ++m) gam[m] = 2.0 * sg[m] / M2;
+        }
+        for (int m = 0; m < B; ++m) {
+            double* o = out + (size_t)m * NIWQG_S_COUNT;
+            const double* s = &ss[(size_t)m * QS_COUNT];
+            for (int k = 0; k < NIWQG_S_COUNT; ++k) o[k] = 0.0;
+            o[NIWQG_S_KE] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KE];
+            o[NIWQG_S_CVAR] = ps ? sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_CVAR] : 0.0;
+            o[NIWQG_S_KE_QG] = 0.5 * s[QS_KE] / M2;
+            o[NIWQG_S_ENS] = 0.5 * sq[m] / M;
+            o[NIWQG_S_EP_PSI] = h->p.nu4 * s[QS_QLAP2PSI] / M2 - h->p.nu * s[QS_PLAPQ] / M2 + h->p.mu * s[QS_PQ] / M2;
+            o[NIWQG_S_CHI_Q] = -h->p.nu4 * s[QS_CHIQ] / M2;
+            if (ps) {
+                const double C2 = s[QS_C2] / M2, gradC2 = s[QS_GRADC2] / M2, lapc2 = s[QS_LAPC2] / M2, lap2clapc = s[QS_LAP2CLAPC] / M2;
+                o[NIWQG_S_C2] = C2; o[NIWQG_S_GRADC2] = gradC2; o[NIWQG_S_GAMMA_C] = m < 64 ? gam[m] : 0.0;
+                o[NIWQG_S_EP_C] = -2 * h->p.nu4c * lapc2 - 2 * h->p.nu * gradC2 - 2 * h->p.muc * C2;          // QGModel.py:595-598
+                o[NIWQG_S_CHI_C] = 2 * h->p.nu4c * lap2clapc - 2 * h->p.nu * lapc2 - 2 * h->p.muc * gradC2;  // QGModel.py:600-604
+            }
+        }
+        return 0;
+    }
+    // ---- kernel family: _calc_energy_conversion on the current state (stale phix/phiy for UnCoupled, F6)
+    const bool ybj = (h->flags & MF_YBJ) != 0;
+    if (ybj) {   // lapphi = ifft(-wv2*phih) is recomputed by every _calc_energy_conversion (Kernel.py:685)
+        int r0 = wave_fields(h, false, false, true);
+        if (r0) return r0;
+    }
+    PhysArgs pa = phys_args(h, MF_NO_WRITE);
+    pa.flags &= ~MF_YBJ;   // the tick evaluates the full budget terms for every family model
+    k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+    CK(cudaGetLastError());
+    FIN(SD_COUNT, h->sumsD);
+    int r = ke_qg_family(h);      // spectral sums -> sumsX
+    if (r) return r;
+    // budget terms of the tick use Parseval sums from k_spec_sums: copy into the SE layout
+    CK(cudaMemcpyAsync(ss.data(), h->sumsX, (size_t)B * SS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sd.data(), h->sumsD, (size_t)B * SD_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sc.data(), h->scal, sc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // conc_niw second pass (centred sums)
+    k_qpsi_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->qs, h->npts, h->part);
+    CK(cudaGetLastError());
+    FIN(1, h->sumsE);
+    k_conc_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->qs, h->npts, h->sumsD, h->sumsE, h->part);
+    CK(cudaGetLastError());
+    FIN(3, h->sumsE);
+    CK(cudaMemcpyAsync(s3.data(), h->sumsE, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->launches += 3;
+    // pe_niw: refreshes phix, phiy (Kernel.py:608-611) -- after the conversion terms, as in the registry order
+    r = pe_niw_refresh(h, h->sumsE);
+    if (r) return r;
+    CK(cudaMemcpyAsync(sg.data(), h->sumsE, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const niwqg_params& p = h->p;
+    for (int m = 0; m < B; ++m) {
+        double* o = out + (size_t)m * NIWQG_S_COUNT;
+        const double* D = &sd[(size_t)m * SD_COUNT];
+        const double* S = &ss[(size_t)m * SS_COUNT];
+        for (int k = 0; k < NIWQG_S_COUNT; ++k) o[k] = 0.0;
+        o[NIWQG_S_KE] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KE];
+        o[NIWQG_S_PW] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_PW];
+        o[NIWQG_S_KW] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KW];
+        o[NIWQG_S_GAMMA1] = 0.5 * 0.5 * h->hslash * (D[SD_G1] / M) / p.f;
+        o[NIWQG_S_GAMMA2] = 0.5 * h->hslash * (D[SD_G2] / M) / p.f;
+        o[NIWQG_S_XI1] = (D[SD_X1] / M) / p.f;
+        o[NIWQG_S_XI2] = (D[SD_X2] / M) / p.f;
+        const double ar = D[SD_PHI_R] / M, ai = D[SD_PHI_I] / M, br = D[SD_QPC_R] / M, bi = D[SD_QPC_I] / M;
+        o[NIWQG_S_PI] = 0.5 * (ar * bi + ai * br);
+        o[NIWQG_S_KE_QG] = 0.5 * S[SS_KE] / M2;
+        o[NIWQG_S_ENS] = 0.5 * D[SD_Q2] / M;
+        o[NIWQG_S_KE_NIW] = 0.5 * D[SD_PHI2] / M;
+        o[NIWQG_S_CKE_NIW] = 0.5 * (ar * ar + ai * ai);
+        o[NIWQG_S_IKE_NIW] = o[NIWQG_S_KE_NIW] - o[NIWQG_S_CKE_NIW];
+        const double grad2 = sg[m] / M;     // refreshed phix, phiy
+        o[NIWQG_S_PE_NIW] = 0.25 * grad2 / h->kappa2;
+        const double* c3 = &s3[(size_t)m * 3];
+        o[NIWQG_S_CONC] = (c3[0] / M) / sqrt(c3[1] / M) / sqrt(c3[2] / M);
+        o[NIWQG_S_SKEW] = (D[SD_QP3] / M) / pow(D[SD_QP2] / M, 1.5);
+        const double lap2m = D[SD_LAP2] / M, phi2m = D[SD_PHI2] / M;
+        o[NIWQG_S_EP_PHI] = -p.nu4w * lap2m - p.nuw * grad2 - p.muw * phi2m;
+        if (ybj)   // YBJ never defines p (zeros, YBJModel.py:44): only the q*lap2psi term survives
+            o[NIWQG_S_EP_PSI] = p.nu4 * S[SS_QLAP2PSI] / M2;
+        else
+            o[NIWQG_S_EP_PSI] = p.nu4 * S[SS_QLAP2PSI] / M2 - p.nu * S[SS_PLAPQ] / M2 + p.mu * S[SS_PQ] / M2;
+        o[NIWQG_S_CHI_Q] = -p.nu4 * S[SS_CHIQ] / M2;
+        o[NIWQG_S_CHI_PHI] = -0.5 * p.nu4w * (S[SS_WV6PHI] / M2) / h->kappa2 - 0.5 * p.nuw * lap2m / h->kappa2 -
+                             0.5 * p.muw * grad2 / h->kappa2;
+        if (h->flags & MF_WAVE_PV) {
+            o[NIWQG_S_KE_QG_Q] = 0.5 * S[SS_KEQ] / M2;
+            o[NIWQG_S_KE_QG_W] = 0.5 * S[SS_KEW] / M2;
+            o[NIWQG_S_KE_QG_QW] = S[SS_KEQW] / M2;
+        }
+    }
+    return 0;
+}
+
+size_t niwqg_field_bytes(const niwqg_handle* h, int field) {
+    const size_t r = h->npts * sizeof(double), c = h->npts * sizeof(cd), s = h->nspec * sizeof(cd);
+    switch (field) {
+        case NIWQG_F_Q: case NIWQG_F_P: case NIWQG_F_U: case NIWQG_F_V: case NIWQG_F_QW: case NIWQG_F_QPSI: case NIWQG_F_C:
+            return r;
+        case NIWQG_F_PHI: case NIWQG_F_PHIX: case NIWQG_F_PHIY: case NIWQG_F_LAPPHI: return c;
+        case NIWQG_F_FILTR: return h->nspec * sizeof(double);
+        default: return s;
+    }
+}
+
+int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t bytes, int on_device) {
+    CK(cudaSetDevice(h->p.device));
+    if (member < 0 || member >= h->B) { h->err = "get_field: bad member"; return -1; }
+    if (bytes != niwqg_field_bytes(h, field)) { h->err = "get_field: size mismatch"; return -1; }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t mo = (size_t)member * h->npts, so = (size_t)member * h->nspec;
+    const void* src = nullptr;
+    auto real_of = [&](const cd* f, int which) -> int {
+        if (!f) { h->err = "get_field: field not defined for this model"; return -1; }
+        k_extract_real<<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(f + mo, h->rscratch, h->npts, which);
+        CK(cudaGetLastError());
+        h->launches++;
+        src = h->rscratch;
+        return 0;
+    };
+    int r = 0;
+    switch (field) {
+        case NIWQG_F_Q: r = real_of(h->qs, 0); break;
+        case NIWQG_F_QW: r = real_of(h->qs, 1); break;
+        case NIWQG_F_QPSI: r = real_of(h->qs, 2); break;
+        case NIWQG_F_U: r = real_of(h->uv, 0); break;
+        case NIWQG_F_V: r = real_of(h->uv, 1); break;
+        case NIWQG_F_C: r = real_of(h->p.passive_scalar ? h->W : nullptr, 0); break;
+        case NIWQG_F_P: {
+            // p = Re ifft(ph): on demand, one member, through scratch P1
+            if (h->qg) {
+                QgExpand1Args ea{};
+                ea.N = h->N; ea.nk = h->nk; ea.dk = h->dk; ea.in = h->ph + so; ea.out = h->P1; ea.mode = QGX_PLAIN;
+                k_qg_expand1<<<dim3(NIWQG_PW_BLOCKS, 1), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+                CK(cudaGetLastError());
+                h->launches++;
+                FFT(h->P1, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);
+            } else {
+                FFT(h->ph + so, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);
+            }
+            src = h->rscratch;
+        } break;
+        case NIWQG_F_QH: src = h->qh[h->cq] + so; break;
+        case NIWQG_F_PH: src = h->ph + so; break;
+        case NIWQG_F_PHI: src = h->phi ? h->phi + mo : nullptr; break;
+        case NIWQG_F_PHIH: src = h->phih[h->cp] ? h->phih[h->cp] + so : nullptr; break;
+        case NIWQG_F_PHIX: src = h->phix ? h->phix + mo : nullptr; break;
+        case NIWQG_F_PHIY: src = h->phiy ? h->phiy + mo : nullptr; break;
+        case NIWQG_F_LAPPHI: src = h->lapphi ? h->lapphi + mo : nullptr; break;
+        case NIWQG_F_QWH: src = h->qwh ? h->qwh + so : nullptr; break;
+        case NIWQG_F_CH: src = h->chh[h->cc] ? h->chh[h->cc] + so : nullptr; break;
+        case NIWQG_F_FILTR: src = h->filtr; break;
+        case NIWQG_F_EXPCH: src = h->tq.E; break;
+        case NIWQG_F_EXPCH_H: src = h->tq.E2; break;
+        case NIWQG_F_QHCOEF: src = h->tq.Q; break;
+        case NIWQG_F_F0: src = h->tq.f0; break;
+        case NIWQG_F_FAB: src = h->tq.fab; break;
+        case NIWQG_F_FC: src = h->tq.fc; break;
+        case NIWQG_F_EXPCHW: src = h->tp.E; break;
+        case NIWQG_F_EXPCH_HW: src = h->tp.E2; break;
+        case NIWQG_F_QHWCOEF: src = h->tp.Q; break;
+        case NIWQG_F_F0W: src = h->tp.f0; break;
+        case NIWQG_F_FABW: src = h->tp.fab; break;
+        case NIWQG_F_FCW: src = h->tp.fc; break;
+        case NIWQG_F_EXPCHC: src = h->tc.E; break;
+        case NIWQG_F_EXPCH_HC: src = h->tc.E2; break;
+        case NIWQG_F_QHCCOEF: src = h->tc.Q; break;
+        case NIWQG_F_F0C: src = h->tc.f0; break;
+        case NIWQG_F_FABC: src = h->tc.fab; break;
+        case NIWQG_F_FCC: src = h->tc.fc; break;
+        default: h->err = "get_field: unknown field"; return -1;
+    }
+    if (r) return r;
+    if (!src) { h->err = "get_field: field not defined for this model"; return -1; }
+    CK(cudaMemcpyAsync(dst, src, bytes, kind, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
+    CK(cudaSetDevice(h->p.device));
+    const size_t c = h->npts * sizeof(cd), r = h->npts * sizeof(double);
+    const int N = h->N, nh = N / 2 + 1;
+    switch (kind) {
+        case NIWQG_FFT_C2C_FWD:
+        case NIWQG_FFT_C2C_INV:
+            CK(cudaMemcpyAsync(h->P1, in, c, cudaMemcpyHostToDevice, h->stream));
+            FFT(h->P1, h->P1, kind == NIWQG_FFT_C2C_INV, PRO_NONE, 1);
+            CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
+            break;
+        case NIWQG_FFT_R2C_FULL:
+        case NIWQG_FFT_R2C:
+            CK(cudaMemcpyAsync(h->rscratch, in, r, cudaMemcpyHostToDevice, h->stream));
+            FFT(h->rscratch, h->P1, false, PRO_REAL_IN, 1);
+            if (kind == NIWQG_FFT_R2C_FULL)
+                CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
+            else
+                CK(cudaMemcpy2DAsync(out, nh * sizeof(cd), h->P1, N * sizeof(cd), nh * sizeof(cd), N, cudaMemcpyDeviceToHost,
+                                     h->stream));
+            break;
+        case NIWQG_FFT_C2R: {
+            CK(cudaMemcpyAsync(h->P2, in, (size_t)N * nh * sizeof(cd), cudaMemcpyHostToDevice, h->stream));
+            QgExpand1Args ea{};
+            ea.N = N; ea.nk = nh; ea.dk = h->dk; ea.in = h->P2; ea.out = h->P1; ea.mode = QGX_PLAIN;
+            k_qg_expand1<<<dim3(NIWQG_PW_BLOCKS, 1), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+            CK(cudaGetLastError());
+            h->launches++;
+            FFT(h->P1, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);
+            CK(cudaMemcpyAsync(out, h->rscratch, r, cudaMemcpyDeviceToHost, h->stream));
+        } break;
+        default: h->err = "fft2: unknown kind"; return -1;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int niwqg_jacobian(niwqg_handle* h, int which, void* out) {
+    CK(cudaSetDevice(h->p.device));
+    if (h->B != 1) { h->err = "jacobian: batch==1 only"; return -1; }
+    if (h->qg) {
+        if (which != NIWQG_JAC_PSI_Q) { h->err = "jacobian: QGModel has J(psi,q) only"; return -1; }
+        int r = qg_expand_and_invert(h, h->qh[h->cq]);
+        if (r) return r;
+        k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, nullptr, h->P1, h->P2, h->npts);
+        CK(cudaGetLastError());
+        FFT(h->P1, h->P1, false, PRO_NONE, 1);
+        k_qg_jacobian_out<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->P1, h->P2, h->N, h->nk, h->dk);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        CK(cudaMemcpyAsync(out, h->P2, h->nspec * sizeof(cd), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    const size_t c = h->npts * sizeof(cd);
+    if (which == NIWQG_JAC_PHIC_PHI) {
+        if (!(h->flags & MF_WAVE_PV)) { h->err = "jacobian_phic_phi: Coupled/QL only"; return -1; }
+        int r = wave_fields(h, false, true, false);     // refreshes phix, phiy (CoupledModel.py:70)
+        if (r) return r;
+        k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale);
+        CK(cudaGetLastError());
+        FFT(h->W, h->W, false, PRO_NONE, 1);
+        k_split_packed<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->W, h->P1, h->N, 1, 1, 1.0 / h->jscale);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        // both need the [D] products of the current carried state
+        PhysArgs pa = phys_args(h, 0);
+        pa.flags &= ~MF_YBJ;
+        k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+        CK(cudaGetLastError());
+        h->launches++;
+        if (which == NIWQG_JAC_PSI_Q) {
+            FFT(h->P1, h->P1, false, PRO_NONE, 1);
+            k_jac_psi_q_out<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->P1, h->P2, h->N, h->dk);
+            CK(cudaGetLastError());
+            h->launches++;
+            CK(cudaMemcpyAsync(out, h->P2, c, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            // fft(u phix + v phiy): reuse P1 as scratch for the plain product
+            if (h->flags & MF_QL_ADV) { int r = ql_wave_velocity(h); if (r) return r; }
+            k_adv_product<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(
+                (h->flags & MF_QL_ADV) ? h->uvq : h->uv, h->phix, h->phiy, h->P1, h->npts);
+            CK(cudaGetLastError());
+            FFT(h->P1, h->P1, false, PRO_NONE, 1);
+            if (h->flags & MF_FIX00) CK(cudaMemsetAsync(h->P1, 0, sizeof(cd), h->stream));
+            h->launches++;
+            CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"
