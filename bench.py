@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the niwqg ETDRK4 hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Metric (BASELINE.json): fp64 grid-point-steps/s of the coupled NIW-QG model.
+Default workload: CoupledModel, Lamb dipole + uniform NIW, 8192^2, fp64, exponential filter on
+(the grid the north-star target is stated on; 34.5 GiB resident, so one member per GPU).  With
+N > 1 every rank steps its own independent member (ensemble sharding, no data-path collective):
+weak scaling.  One "step" = one _step_etdrk4 of every member.
+
+Keys beyond the base contract: `roofline` (dominant kernel: the FFT pass, live CUDA-event timing),
+`step_roofline` (whole step against the algorithmic 3392 B/point model of SURVEY.md section 8d),
+`kernel_breakdown`, `cpu_baseline` (the numpy oracle port timed on this box, N=1 only), `parity`.
+
+`--impl reference` times the reference's CPU implementation of the same path (the numpy oracle port,
+bit-identical to the reference; the reference itself is pure Python + numpy) on the host cores.
+"""
+import argparse
+import json
+import logging
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+METRIC = "fp64 grid-point-steps/sec (coupled NIW-QG)"
+UNIT = "grid-point-steps/s"
+B_ALG_COUPLED = 3392.0        # algorithmic bytes per grid point per step
+FFT_PASS_BYTES_PER_POINT = 32.0   # one pass of a c128 2-D FFT: read 16 B + write 16 B
+
+WORKLOADS = {
+    # name: (model, nx, batch)
+    "coupled8192": ("coupled", 8192, 1),
+    "coupled4096": ("coupled", 4096, 1),
+    "coupled2048": ("coupled", 2048, 1),
+    "coupled512_ens8": ("coupled", 512, 8),     # BASELINE.json config 5: 8 members of 512^2 per GPU
+    "coupled512": ("coupled", 512, 1),          # BASELINE.json config 2 (fits in L2: not an HBM measurement)
+}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_params(nx):
+    from cases import lamb_params
+    kw, U0, k0 = lamb_params(nx, True, 10 ** 9, 1)
+    kw["tmax"] = 1e30
+    kw["twrite"] = 10 ** 9
+    return kw, U0, k0
+
+
+def initial_conditions(model, U0, k0, batch, seed0=0):
+    """Lamb dipole (+ a member-dependent random-spectrum perturbation for ensembles) and a uniform NIW."""
+    from niwqg_b200 import InitialConditions as ic
+    q = ic.LambDipole(model, U=U0, R=2 * np.pi / k0)
+    if batch > 1:
+        rng = np.random.RandomState(1234 + seed0)
+        q = np.stack([q * (1.0 + 0.01 * b) + 1e-3 * np.abs(q).max() * rng.randn(*q.shape) for b in range(batch)])
+    phi = (np.ones(q.shape) + 1j) * (2 * U0) / np.sqrt(2)
+    return q, phi
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # under load = samples in the upper half of the power range
+            thr = 0.5 * (max(pw) + min(pw)) if pw else 0
+            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+def run_ours(args):
+    logging.disable(logging.CRITICAL)
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    from niwqg_b200 import CoupledModel, _native as nat
+
+    model_name, nx, batch = WORKLOADS[args.workload]
+    kw, U0, k0 = workload_params(nx)
+    kw_e2e = dict(kw)
+    kw_e2e["tdiags"] = 1
+    m = CoupledModel.Model(batch=batch, device=local, **kw_e2e)
+    q, phi = initial_conditions(m, U0, k0, batch, seed0=rank)
+    # pinned host buffers (torch is used for pinned/host plumbing and the process group only)
+    q_pin = torch.empty(q.shape, dtype=torch.float64).pin_memory()
+    phi_pin = torch.empty(phi.shape, dtype=torch.complex128).pin_memory()
+    q_pin.numpy()[...] = q
+    phi_pin.numpy()[...] = phi
+    qo_pin = torch.empty((nx, nx), dtype=torch.float64).pin_memory()
+    po_pin = torch.empty((nx, nx), dtype=torch.complex128).pin_memory()
+    del q, phi
+    m.set_q(q_pin.numpy())
+    m.set_phi(phi_pin.numpy())
+    h = m._h
+    npts = batch * nx * nx
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        h.sync()
+
+    # ---------------- device-resident throughput: K steps, inputs already in HBM
+    h.step(args.warmup)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = h.launch_count()
+    ms = h.time_steps(args.steps)
+    l1 = h.launch_count()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * npts * args.steps / (ms * 1e-3)
+
+    # ---------------- per-kernel-kind timing (separate short run with events around every launch)
+    nprof = min(args.steps, 3)
+    h.profile(True)
+    h.step(nprof)
+    prof = h.profile(False)
+
+    # ---------------- end to end through the public Python API, host buffers both ways
+    def e2e_step():
+        m.set_q(q_pin.numpy())                 # H2D + inversion (Kernel.set_q)
+        m.set_phi(phi_pin.numpy())             # H2D (Kernel.set_phi)
+        m._step_forward()                      # step + diagnostics tick (scalars D2H) + status
+        for b in range(batch if batch <= 1 else 1):
+            h.field_into("Q", qo_pin.numpy(), b)       # snapshot of the result, D2H
+            h.field_into("PHI", po_pin.numpy(), b)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ne = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * npts * ne / e2e_s
+    h2d = npts * 8 + npts * 16
+    d2h = nx * nx * 24 + nat.S_COUNT * 8 * batch
+    diag_ke = m.diagnostics["ke_qg"]["value"]
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    # dominant kernel = the FFT pass (row + column launches are the same kernel template)
+    fft_ms = prof["fft_row"][0] + prof["fft_col"][0]
+    fft_n = prof["fft_row"][1] + prof["fft_col"][1]
+    total_prof = sum(v[0] for v in prof.values())
+    dom = max(("fft_row", "fft_col"), key=lambda k: prof[k][0] / max(prof[k][1], 1))
+    pass_bytes = FFT_PASS_BYTES_PER_POINT * npts
+    achieved = pass_bytes / (fft_ms / fft_n * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CoupledModel Lamb dipole + uniform NIW %d^2 fp64, exponential filter, %d member(s)/GPU (%s)"
+                               % (nx, batch, args.workload),
+                   "parallelism": "ensemble: one member batch per GPU, no data-path collective" if world > 1 else "single GPU",
+                   "l2": "working set %.1f GiB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
+                         % (batch * nx * nx * 16 * 34.5 / 2 ** 30) if nx * nx * batch * 16 * 30 > 4e8 else
+                         "working set fits in L2: not an HBM-bound measurement"},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": ne, "what": "per step: set_q + set_phi from pinned host arrays, _step_forward() with the "
+                                     "diagnostics tick (scalars to host), q and phi copied back to pinned host arrays"},
+        "gpu_launches": int(l1 - l0),
+        "roofline": {"bound": "hbm", "kernel": "k_fft_pass (row+column passes of the fp64 2-D FFT)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_launch": pass_bytes,
+                     "avg_launch_ms": fft_ms / fft_n, "slowest_pass": dom,
+                     "row_pass_gbs": pass_bytes / (prof["fft_row"][0] / max(prof["fft_row"][1], 1) * 1e-3) / 1e9,
+                     "col_pass_gbs": pass_bytes / (prof["fft_col"][0] / max(prof["fft_col"][1], 1) * 1e-3) / 1e9,
+                     "share_of_step": fft_ms / total_prof},
+        "step_roofline": {"bytes_per_point_step": B_ALG_COUPLED, "achieved": B_ALG_COUPLED * value / world / 1e9,
+                          "peak": peak, "unit": "GB/s", "frac": B_ALG_COUPLED * value / world / 1e9 / peak},
+        "kernel_breakdown": {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof} for k, v in prof.items()},
+        "sanity": {"ke_qg_last": float(np.ravel(diag_ke)[-1]), "finite": bool(np.all(np.isfinite(diag_ke)))},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(budget_s=25.0)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _oracle_model(nx):
+    from oracle import niwqg_oracle as orc
+    kw, U0, k0 = workload_params(nx)
+    kw.pop("tdiags", None)
+    o = orc.NIWQGOracle(model="coupled", tdiags=10 ** 9, **kw)
+    q = orc.lamb_dipole(o, U=U0, R=2 * np.pi / k0)
+    o.set_q(q)
+    o.set_phi((np.ones_like(q) + 1j) * (2 * U0) / np.sqrt(2))
+    return o
+
+
+def cpu_baseline(budget_s=25.0, nx=None, steps=None):
+    """The numpy oracle port (bit-identical to the reference) timed on this box, one core (numpy's FFT and
+    ufuncs are single-threaded).  Bounded sample of the same workload: same model, parameters scaled the same
+    way, smaller grid - the metric is per grid point."""
+    if nx is None:
+        nx = 1024 if budget_s >= 20 else 512
+    per_step = {256: 0.3, 512: 1.3, 1024: 6.5}.get(nx, 6.5)
+    if steps is None:
+        steps = max(2, int(budget_s / per_step))
+    o = _oracle_model(nx)
+    o.step()                                   # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step()
+    dt = time.perf_counter() - t0
+    return {"value": nx * nx * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "host_cores_available": os.cpu_count(),
+            "sample": "CoupledModel Lamb dipole + uniform NIW %d^2 (same parameters scaled to the grid), %d steps of "
+                      "oracle/niwqg_oracle.py (numpy, bit-identical to the reference), %.1f s" % (nx, steps, dt)}
+
+
+def _ref_worker(nx, steps, warm, q):
+    o = _oracle_model(nx)
+    for _ in range(warm):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step()
+    q.put(time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (numpy; oracle port), using all the host
+    threads it can: the solver itself is single-threaded, so the box's cores are used the only way the
+    reference can use them - independent single-threaded replicas (an ensemble) run concurrently."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    total_steps = args.steps + args.warmup
+    # bounded sample: keep the whole run within a few minutes
+    nx = 1024 if total_steps * 6.5 <= 150 else (512 if total_steps * 1.3 <= 150 else 256)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    mem_per = {256: 0.3, 512: 1.2, 1024: 4.5}[nx] * 2 ** 30
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except Exception:
+        avail = 8 * 2 ** 30
+    nproc = int(max(1, min(cores, 32, avail * 0.6 // mem_per)))
+    ctx = mp.get_context("fork")
+    qq = ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=(nx, args.steps, args.warmup, qq)) for _ in range(nproc)]
+    for p in procs:
+        p.start()
+    times = [qq.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = max(times)
+    value = nproc * nx * nx * args.steps / wall
+    sample = ("%d concurrent single-threaded replicas of CoupledModel Lamb dipole + uniform NIW %d^2, %d steps each "
+              "(oracle/niwqg_oracle.py = the reference's numpy arithmetic), %.1f s" % (nproc, nx, args.steps, wall))
+    model_name, nx_w, batch = WORKLOADS[args.workload]
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "CoupledModel Lamb dipole + uniform NIW %d^2 fp64 (%s); CPU arm times a bounded %d^2 sample"
+                                  % (nx_w, args.workload, nx)},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "port", "sample": sample,
+                            "single_replica_value": nx * nx * args.steps / float(np.mean(times))},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="coupled8192", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -136,6 +136,11 @@ int niwqg_jacobian(niwqg_handle* h, int which, void* out);
 int niwqg_sync(niwqg_handle* h);
 /* CUDA-event timing on the handle's stream: elapsed ms of `nsteps` steps */
 int niwqg_time_steps(niwqg_handle* h, int nsteps, float* ms);
+/* per-kernel-kind CUDA-event timing on the handle's stream.  Reads the records accumulated since the
+ * last call into ms_out[5] / count_out[5] (kinds: 0 FFT row pass, 1 FFT column pass, 2 physical-space
+ * pointwise, 3 spectral pointwise, 4 small reductions), clears them and switches recording on/off.
+ * ms_out/count_out may be NULL. */
+int niwqg_profile(niwqg_handle* h, int enable, double* ms_out, long long* count_out);
 /* number of kernel launches issued by this handle so far */
 long long niwqg_launch_count(const niwqg_handle* h);
 /* the cudaStream_t the handle launches on (for external event timing) */

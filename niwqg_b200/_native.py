@@ -36,7 +36,7 @@ JAC_PSI_Q, JAC_PHIC_PHI, JAC_PSI_PHI = range(3)
 EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "niwqg_set_phi", "niwqg_set_c",
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
-           "niwqg_launch_count", "niwqg_stream"]
+           "niwqg_launch_count", "niwqg_stream", "niwqg_profile"]
 
 
 class Params(C.Structure):
@@ -78,6 +78,7 @@ def load():
     lib.niwqg_time_steps.argtypes = [vp, ip, C.POINTER(C.c_float)]
     lib.niwqg_launch_count.argtypes = [vp]
     lib.niwqg_launch_count.restype = C.c_longlong
+    lib.niwqg_profile.argtypes = [vp, ip, vp, vp]
     lib.niwqg_stream.argtypes = [vp]
     lib.niwqg_stream.restype = vp
     _lib = lib
@@ -161,6 +162,20 @@ class Handle(object):
 
     def sync(self):
         self._ck(self.lib.niwqg_sync(self.h))
+
+    PROFILE_KINDS = ("fft_row", "fft_col", "phys", "spec", "small")
+
+    def profile(self, enable):
+        """Switch per-kernel-kind event timing on/off; returns {kind: (total_ms, launches)} recorded so far."""
+        ms = np.zeros(5)
+        cnt = np.zeros(5, np.int64)
+        self._ck(self.lib.niwqg_profile(self.h, int(bool(enable)), ms.ctypes.data, cnt.ctypes.data))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def field_into(self, name, out, member=0):
+        """Copy one member's field into a caller-provided (e.g. pinned) host array."""
+        self._ck(self.lib.niwqg_get_field(self.h, F[name], member, out.ctypes.data, out.nbytes, 0))
+        return out
 
     def launch_count(self):
         return int(self.lib.niwqg_launch_count(self.h))

@@ -61,7 +61,34 @@ struct niwqg_handle {
     // reductions
     double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *scal = nullptr, *stagev = nullptr;
     bool q_set = false, phi_set = false;
+    // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg)
+    bool prof = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
 };
+
+enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COUNT };
+
+static cudaEvent_t prof_event(niwqg_handle* h) {
+    if (h->prof_used == h->prof_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_pool.push_back(e);
+    }
+    return h->prof_pool[h->prof_used++];
+}
+struct ProfScope {
+    niwqg_handle* h; int kind; cudaEvent_t a;
+    ProfScope(niwqg_handle* h_, int k) : h(h_), kind(k), a(nullptr) {
+        if (h->prof) { a = prof_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~ProfScope() {
+        if (h->prof) { cudaEvent_t b = prof_event(h); cudaEventRecord(b, h->stream); h->prof_recs.push_back({kind, a, b}); }
+    }
+};
+#define PROF(kind) ProfScope prof_scope__(h, kind)
 
 // ---------------------------------------------------------------------------
 static int dalloc(niwqg_handle* h, void** p, size_t bytes, bool zero = true) {
@@ -99,12 +126,12 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     // pass 1: rows
     a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE;
     a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0;
-    CK(launch_pass<false>(h->N, a, batch, h->stream));
+    { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
     // pass 2: columns
     a.in = out; a.out = (epi == EPI_REAL_OUT) ? real_out : (void*)out; a.pro = PRO_NONE; a.epi = epi;
     a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
     a.scale = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
-    CK(launch_pass<true>(h->N, a, batch, h->stream));
+    { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, batch, h->stream)); }
     h->launches += 2;
     return 0;
 }
@@ -115,6 +142,7 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     } while (0)
 
 static int finalize(niwqg_handle* h, int K, double* out, int is_max = 0) {
+    PROF(PK_SMALL);
     k_finalize<<<h->B, 32, 0, h->stream>>>(h->part, NIWQG_PW_BLOCKS, K, out, is_max);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -193,14 +221,14 @@ static int invert_family(niwqg_handle* h) {
     ia.flags = h->flags; ia.f = h->p.f; ia.qh = h->qh[h->cq]; ia.filtr = h->filtr;
     ia.ph = h->ph; ia.qs = h->qs;
     if (h->flags & MF_WAVE_PV) {
-        k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale);
+        { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
         CK(cudaGetLastError());
         h->launches++;
         FFT(h->W, h->W, false, PRO_NONE, h->B);
         ia.W = h->W; ia.qwh = h->qwh; ia.inv_jscale = 1.0 / h->jscale;
     }
     if (h->flags & MF_YBJ) ia.uvgen = h->uv;
-    k_spec_invert<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ia);
+    { PROF(PK_SPEC); k_spec_invert<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ia); }
     CK(cudaGetLastError());
     h->launches++;
     if (h->flags & MF_YBJ) {
@@ -223,7 +251,7 @@ static PhysArgs phys_args(niwqg_handle* h, int extra_flags) {
 }
 
 static int ql_wave_velocity(niwqg_handle* h) {   // uq, vq from the current qh (QLModel.py:65-66)
-    k_spec_uvq<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(Grid{h->N, h->dk}, h->qh[h->cq], h->uvq);
+    { PROF(PK_SPEC); k_spec_uvq<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(Grid{h->N, h->dk}, h->qh[h->cq], h->uvq); }
     CK(cudaGetLastError());
     h->launches++;
     FFT(h->uvq, h->uvq, true, PRO_NONE, h->B);
@@ -249,7 +277,7 @@ static int step_family(niwqg_handle* h) {
         sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
         if (!ql) {
             PhysArgs pa = phys_args(h, 0);
-            k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+            { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
             CK(cudaGetLastError());
             h->launches++;
             if (!ybj) {
@@ -257,7 +285,7 @@ static int step_family(niwqg_handle* h) {
                 FFT(h->P1, h->P1, false, PRO_NONE, h->B);
             }
             FFT(h->P2, h->P2, false, PRO_NONE, h->B);
-            k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+            { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
             CK(cudaGetLastError());
             h->launches++;
             if (st == 1) { h->cq = nq; h->cp = np; }
@@ -265,29 +293,29 @@ static int step_family(niwqg_handle* h) {
             // repaired QL: jacobian_psi_phi reads qh AFTER the stage's q update (Kernel.py:326-332 order),
             // so the stage is split: q half, wave velocity from the new qh, phi half.
             PhysArgs pa = phys_args(h, MF_SKIP_P2);
-            k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+            { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
             CK(cudaGetLastError());
             FIN(SD_COUNT, h->sumsD);
             FFT(h->P1, h->P1, false, PRO_NONE, h->B);
             sa.do_phi = 0;
-            k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+            { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
             CK(cudaGetLastError());
             if (st == 1) h->cq = nq;
             int r = ql_wave_velocity(h);
             if (r) return r;
             pa = phys_args(h, MF_SKIP_P1);
-            k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+            { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
             CK(cudaGetLastError());
             FFT(h->P2, h->P2, false, PRO_NONE, h->B);
             sa.do_q = 0; sa.do_phi = 1;
-            k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+            { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
             CK(cudaGetLastError());
             h->launches += 4;
             if (st == 1) h->cp = np;
         }
         if (!ybj) {
             FIN(SE_COUNT, h->sumsE);
-            k_budget<<<h->B, 32, 0, h->stream>>>(budget_args(h, st));
+            { PROF(PK_SMALL); k_budget<<<h->B, 32, 0, h->stream>>>(budget_args(h, st)); }
             CK(cudaGetLastError());
             h->launches++;
             // self.phi = ifft(phih); _invert(); _calc_rel_vorticity()  (Kernel.py:337-339 / :395-397)
@@ -308,7 +336,7 @@ static int step_family(niwqg_handle* h) {
 static int qg_expand_and_invert(niwqg_handle* h, const cd* qh_cur, bool want_uv = true) {
     QgExpandArgs ea{};
     ea.N = h->N; ea.nk = h->nk; ea.dk = h->dk; ea.qh = qh_cur; ea.ph = h->ph; ea.uv = want_uv ? h->uv : nullptr; ea.qs = h->qs;
-    k_qg_expand<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+    { PROF(PK_SPEC); k_qg_expand<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ea); }
     CK(cudaGetLastError());
     h->launches++;
     if (want_uv) FFT(h->uv, h->uv, true, PRO_NONE, h->B);
@@ -319,7 +347,7 @@ static int qg_expand_and_invert(niwqg_handle* h, const cd* qh_cur, bool want_uv 
 static int qg_scalar_physical(niwqg_handle* h, const cd* ch_cur) {
     QgExpand1Args ea{};
     ea.N = h->N; ea.nk = h->nk; ea.dk = h->dk; ea.in = ch_cur; ea.out = h->W; ea.mode = QGX_PLAIN;
-    k_qg_expand1<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+    { PROF(PK_SPEC); k_qg_expand1<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ea); }
     CK(cudaGetLastError());
     h->launches++;
     FFT(h->W, h->W, true, PRO_NONE, h->B);
@@ -340,8 +368,8 @@ static int step_qg(niwqg_handle* h) {
             r = qg_scalar_physical(h, ccur);       // c = irfft2(ch) -> W.x   (QGModel.py:493)
             if (r) return r;
         }
-        k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, ps ? h->W : nullptr, h->P1, h->P2,
-                                                                       h->npts);
+        { PROF(PK_PHYS); k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, ps ? h->W : nullptr, h->P1, h->P2,
+                                                                       h->npts); }
         CK(cudaGetLastError());
         h->launches++;
         FFT(h->P1, h->P1, false, PRO_NONE, h->B);
@@ -353,7 +381,7 @@ static int step_qg(niwqg_handle* h) {
         sa.y0c = h->chh[oc]; sa.yc = h->chh[nc]; sa.y1c = h->y1c; sa.F0c = h->F0c; sa.Fabc = h->Fabc;
         sa.tq = h->tq; sa.tc = h->tc; sa.filtr = h->filtr; sa.partials = h->part;
         sa.nu4c = h->p.nu4c;
-        k_qg_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa);
+        { PROF(PK_SPEC); k_qg_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
         CK(cudaGetLastError());
         h->launches++;
         if (st == 1) { h->cq = nq; h->cc = nc; }
@@ -362,7 +390,7 @@ static int step_qg(niwqg_handle* h) {
         ba.stage = st; ba.M = (double)h->npts; ba.dt = h->p.dt; ba.nu4 = h->p.nu4; ba.nu = h->p.nu; ba.mu = h->p.mu;
         ba.nu4c = h->p.nu4c; ba.muc = h->p.muc; ba.ps = ps ? 1 : 0;
         ba.sumsE = h->sumsE; ba.scal = h->scal; ba.stagev = h->stagev;
-        k_qg_budget<<<h->B, 32, 0, h->stream>>>(ba);
+        { PROF(PK_SMALL); k_qg_budget<<<h->B, 32, 0, h->stream>>>(ba); }
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -378,7 +406,7 @@ static int step_qg(niwqg_handle* h) {
 static int qg_gamma_c(niwqg_handle* h) {
     int r = qg_scalar_physical(h, h->chh[h->cc]);      // jacobian_psi_c refreshes c = irfft2(ch) (QGModel.py:493)
     if (r) return r;
-    k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, h->W, h->P1, h->P2, h->npts);
+    { PROF(PK_PHYS); k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, h->W, h->P1, h->P2, h->npts); }
     CK(cudaGetLastError());
     FFT(h->P2, h->P2, false, PRO_NONE, h->B);
     k_qg_gamma_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->P2, h->chh[h->cc], h->N, h->nk, h->dk, h->part);
@@ -400,6 +428,7 @@ int niwqg_destroy(niwqg_handle* h) {
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -686,6 +715,24 @@ int niwqg_time_steps(niwqg_handle* h, int nsteps, float* ms) {
     return 0;
 }
 
+int niwqg_profile(niwqg_handle* h, int enable, double* ms_out, long long* count_out) {
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ms_out && count_out) {
+        for (int k = 0; k < PK_COUNT; ++k) { ms_out[k] = 0.0; count_out[k] = 0; }
+        for (auto& r : h->prof_recs) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, r.a, r.b));
+            ms_out[r.kind] += ms;
+            count_out[r.kind] += 1;
+        }
+    }
+    h->prof_recs.clear();
+    h->prof_used = 0;
+    h->prof = enable != 0;
+    return 0;
+}
+
 int niwqg_get_scalars(niwqg_handle* h, double* out) {
     CK(cudaSetDevice(h->p.device));
     CK(cudaMemcpyAsync(out, h->scal, (size_t)h->B * NIWQG_S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -805,7 +852,7 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
     }
     PhysArgs pa = phys_args(h, MF_NO_WRITE);
     pa.flags &= ~MF_YBJ;   // the tick evaluates the full budget terms for every family model
-    k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+    { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
     CK(cudaGetLastError());
     FIN(SD_COUNT, h->sumsD);
     int r = ke_qg_family(h);      // spectral sums -> sumsX
@@ -910,7 +957,7 @@ int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t by
             if (h->qg) {
                 QgExpand1Args ea{};
                 ea.N = h->N; ea.nk = h->nk; ea.dk = h->dk; ea.in = h->ph + so; ea.out = h->P1; ea.mode = QGX_PLAIN;
-                k_qg_expand1<<<dim3(NIWQG_PW_BLOCKS, 1), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+                { PROF(PK_SPEC); k_qg_expand1<<<dim3(NIWQG_PW_BLOCKS, 1), NIWQG_PW_THREADS, 0, h->stream>>>(ea); }
                 CK(cudaGetLastError());
                 h->launches++;
                 FFT(h->P1, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);
@@ -981,7 +1028,7 @@ int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
             CK(cudaMemcpyAsync(h->P2, in, (size_t)N * nh * sizeof(cd), cudaMemcpyHostToDevice, h->stream));
             QgExpand1Args ea{};
             ea.N = N; ea.nk = nh; ea.dk = h->dk; ea.in = h->P2; ea.out = h->P1; ea.mode = QGX_PLAIN;
-            k_qg_expand1<<<dim3(NIWQG_PW_BLOCKS, 1), NIWQG_PW_THREADS, 0, h->stream>>>(ea);
+            { PROF(PK_SPEC); k_qg_expand1<<<dim3(NIWQG_PW_BLOCKS, 1), NIWQG_PW_THREADS, 0, h->stream>>>(ea); }
             CK(cudaGetLastError());
             h->launches++;
             FFT(h->P1, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);
@@ -1000,7 +1047,7 @@ int niwqg_jacobian(niwqg_handle* h, int which, void* out) {
         if (which != NIWQG_JAC_PSI_Q) { h->err = "jacobian: QGModel has J(psi,q) only"; return -1; }
         int r = qg_expand_and_invert(h, h->qh[h->cq]);
         if (r) return r;
-        k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, nullptr, h->P1, h->P2, h->npts);
+        { PROF(PK_PHYS); k_qg_products<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->qs, nullptr, h->P1, h->P2, h->npts); }
         CK(cudaGetLastError());
         FFT(h->P1, h->P1, false, PRO_NONE, 1);
         k_qg_jacobian_out<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->P1, h->P2, h->N, h->nk, h->dk);
@@ -1015,7 +1062,7 @@ int niwqg_jacobian(niwqg_handle* h, int which, void* out) {
         if (!(h->flags & MF_WAVE_PV)) { h->err = "jacobian_phic_phi: Coupled/QL only"; return -1; }
         int r = wave_fields(h, false, true, false);     // refreshes phix, phiy (CoupledModel.py:70)
         if (r) return r;
-        k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale);
+        { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
         CK(cudaGetLastError());
         FFT(h->W, h->W, false, PRO_NONE, 1);
         k_split_packed<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->W, h->P1, h->N, 1, 1, 1.0 / h->jscale);
@@ -1026,7 +1073,7 @@ int niwqg_jacobian(niwqg_handle* h, int which, void* out) {
         // both need the [D] products of the current carried state
         PhysArgs pa = phys_args(h, 0);
         pa.flags &= ~MF_YBJ;
-        k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa);
+        { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
         CK(cudaGetLastError());
         h->launches++;
         if (which == NIWQG_JAC_PSI_Q) {
