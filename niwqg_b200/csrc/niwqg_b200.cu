@@ -43,7 +43,7 @@ struct niwqg_handle {
     // tables
     TableSet tq{}, tp{}, tc{};
     double* filtr = nullptr;
-    cd* tw = nullptr;
+    cd *tw_row = nullptr, *tw_col = nullptr, *twc = nullptr;   // stage twiddles of the row / column local length, w_N^t
     // spectral state (c2c family: [B][N][N]; QG: [B][N][nk])
     cd* qh[2] = {nullptr, nullptr};
     cd* phih[2] = {nullptr, nullptr};
@@ -61,6 +61,7 @@ struct niwqg_handle {
     // reductions
     double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *scal = nullptr, *stagev = nullptr;
     bool q_set = false, phi_set = false;
+    int pf_ctas = 296;          // L2 prefetch distance of the FFT passes in CTAs (~ one resident wave: 148 SMs x 2)
     // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg)
     bool prof = false;
     struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -121,14 +122,15 @@ static void build_twiddles(int N, std::vector<cd>& tw) {
 static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro, int batch, int epi = EPI_NONE,
                 void* real_out = nullptr) {
     FftArgs a{};
-    a.tw = h->tw;
+    a.twc = h->twc;
     a.dk = h->dk;
+    a.pf_groups = h->pf_ctas;
     // pass 1: rows
-    a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE;
+    a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row;
     a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0;
     { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
     // pass 2: columns
-    a.in = out; a.out = (epi == EPI_REAL_OUT) ? real_out : (void*)out; a.pro = PRO_NONE; a.epi = epi;
+    a.in = out; a.out = (epi == EPI_REAL_OUT) ? real_out : (void*)out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col;
     a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
     a.scale = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
     { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, batch, h->stream)); }
@@ -440,6 +442,7 @@ static int create_impl(niwqg_handle* h) {
     const niwqg_params& p = h->p;
     const int N = p.nx;
     CK(cudaSetDevice(p.device));
+    if (const char* e = getenv("NIWQG_PF_CTAS")) h->pf_ctas = atoi(e);   // tuning knob (0 = no prefetch)
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -467,11 +470,26 @@ static int create_impl(niwqg_handle* h) {
     const size_t B = h->B, cb = sizeof(cd);
     const size_t fsz = B * h->npts * cb, ssz = B * h->nspec * cb, tsz = h->nspec * cb;
     // twiddles
-    std::vector<cd> tw;
-    build_twiddles(N, tw);
-    DA(h->tw, tw.size() * cb);
-    CK(cudaMemcpyAsync(h->tw, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    {
+        std::vector<cd> tw;
+        build_twiddles(pass_local_len(N, false), tw);
+        DA(h->tw_row, tw.size() * cb);
+        CK(cudaMemcpyAsync(h->tw_row, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        build_twiddles(pass_local_len(N, true), tw);
+        DA(h->tw_col, tw.size() * cb);
+        CK(cudaMemcpyAsync(h->tw_col, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        tw.resize(N);
+        const long double PI = 3.141592653589793238462643383279502884L;
+        for (int t = 0; t < N; ++t) {
+            const long double a = -2.0L * PI * (long double)t / (long double)N;
+            tw[t] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        DA(h->twc, tw.size() * cb);
+        CK(cudaMemcpyAsync(h->twc, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     // tables
     auto alloc_tables = [&](TableSet& t) -> int {
         DA(t.E, tsz); DA(t.E2, tsz); DA(t.Q, tsz); DA(t.f0, tsz); DA(t.fab, tsz); DA(t.fc, tsz);

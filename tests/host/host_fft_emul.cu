@@ -63,8 +63,51 @@ template <int N> double test() {
     return sqrt(err / nrm);
 }
 
+// Cluster decimation-in-time split of fft2d.cuh: C CTAs run local M-point transforms of x[C m + c], multiply by
+// w_N^{c k}, and CTA c' finishes k in [c' M/C, (c'+1) M/C) with a radix-C butterfly over the C partial results.
+template <int M, int C> double test_cluster() {
+    constexpr int N = M * C;
+    std::vector<cd> x(N), out(N), tw, twc(N);
+    build_tw<M>(tw);
+    for (int t = 0; t < N; ++t) {
+        long double a = -2.0L * 3.141592653589793238462643383279502884L * t / N;
+        twc[t] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    for (int i = 0; i < N; ++i) x[i] = make_double2(sin(0.37 * i * i + 1.0), cos(1.3 * i) + 0.01 * i);
+    std::vector<std::vector<cd>> park(C, std::vector<cd>(phys_len(M) + 16));
+    for (int c = 0; c < C; ++c) {
+        std::vector<cd> regs(M), smem(phys_len(M) + 16), loc(M);
+        for (int j = 0; j < M / E; ++j) for (int e = 0; e < E; ++e) regs[j * E + e] = x[C * (j + e * (M / E)) + c];
+        Run<M, 1>::go(regs, smem, loc, tw.data());
+        for (int k = 0; k < M; ++k) park[c][phys(k)] = cmul(loc[k], twc[c * k]);
+    }
+    for (int c = 0; c < C; ++c)
+        for (int g = 0; g < M / C; ++g) {
+            const int k = c * (M / C) + g;
+            cd v[16];
+            for (int r = 0; r < C; ++r) v[r] = park[r][phys(k)];
+            dft<C, 1>(v);
+            for (int p = 0; p < C; ++p) out[k + M * outidx<C>(p)] = v[p];
+        }
+    double err = 0, nrm = 0;
+    int step = N > 512 ? N / 97 : 1;
+    for (int k = 0; k < N; k += step) {
+        long double sr = 0, si = 0;
+        for (int n = 0; n < N; ++n) {
+            long double a = -2.0L * 3.141592653589793238462643383279502884L * ((long long)k * n % N) / N;
+            long double c = cosl(a), s = sinl(a);
+            sr += x[n].x * c - x[n].y * s; si += x[n].x * s + x[n].y * c;
+        }
+        err += (out[k].x - sr) * (out[k].x - sr) + (out[k].y - si) * (out[k].y - si);
+        nrm += sr * sr + si * si;
+    }
+    return sqrt(err / nrm);
+}
+
 int main() {
     int bad = 0;
+#define TC(M, C) { double e = test_cluster<M, C>(); printf("M=%5d C=%d rel err %.3e\n", M, C, e); if (!(e < 1e-14)) bad = 1; }
+    TC(1024, 2) TC(1024, 4) TC(1024, 8) TC(4096, 2)
 #define T(N) { double e = test<N>(); printf("N=%5d rel err %.3e\n", N, e); if (!(e < 1e-14)) bad = 1; }
     T(32) T(64) T(128) T(256) T(512) T(1024) T(2048) T(4096) T(8192)
     return bad;

@@ -1,0 +1,56 @@
+"""CPU-side checks of the host logic: the FFT engine's index maps replayed on the CPU (including the
+thread-block-cluster decimation split), and that the C-ABI library loads and exports every symbol that
+include/niwqg_b200.h declares.  No compute calls: there is no GPU in the build container."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_fft_index_maps_on_cpu(tmp_path):
+    exe = str(tmp_path / "host_fft_emul")
+    subprocess.check_call([NVCC, "-O1", "-Wno-deprecated-gpu-targets", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "host_fft_emul.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "C=8" in out.stdout and "N= 8192" in out.stdout
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from niwqg_b200 import _native
+    lib = _native.load()
+    header = open(os.path.join(ROOT, "include", "niwqg_b200.h")).read()
+    declared = set(re.findall(r"\b(niwqg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libniwqg_b200.so does not export %s" % name
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+
+
+def test_no_cpu_fallback_without_device():
+    """The product path must fail loudly when there is no CUDA device (no oracle / numpy fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import logging
+    logging.disable(logging.CRITICAL)
+    from niwqg_b200 import CoupledModel
+    with pytest.raises(RuntimeError):
+        CoupledModel.Model(nx=64)
+
+
+def test_product_path_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "niwqg_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\S*oracle", src, re.M), "%s imports the oracle" % f
+                assert "niwqg_oracle" not in src, "%s references the oracle module" % f
