@@ -55,45 +55,33 @@ struct FftArgs {
     const cd* twc;    // w_N^t, t = 0..N-1: cluster twiddles (C > 1 only)
     int pro, epi;
     int conj_in, conj_out;
-    double scale;
+    double scale, scale_im;   // output multipliers of the real / imaginary part (scale_im = -scale: conjugate)
     double dk;
     int pf_groups;    // L2 prefetch distance in line groups (0 = off)
+    int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel
 };
 
-template <int N>
-__device__ __forceinline__ cd fft_load(const FftArgs& a, size_t mbase, int row, int col) {
-    const size_t idx = mbase + (size_t)row * N + col;
-    cd x;
-    if (a.pro == PRO_REAL_IN) {
-        x = make_double2(((const double*)a.in)[idx], 0.0);
-    } else {
-        x = ((const cd*)a.in)[idx];
-        if (a.pro != PRO_NONE) {
-            const double k = a.dk * (double)sidx(col, N), l = a.dk * (double)sidx(row, N);
-            switch (a.pro) {
-                case PRO_IK: x = make_double2(-k * x.y, k * x.x); break;
-                case PRO_IL: x = make_double2(-l * x.y, l * x.x); break;
-                case PRO_NEG_WV2: { double w = -(k * k + l * l); x = make_double2(w * x.x, w * x.y); } break;
-                case PRO_WV4: { double w = k * k + l * l; w = w * w; x = make_double2(w * x.x, w * x.y); } break;
-                case PRO_UV: {
-                    const double kz = (col == (N >> 1)) ? 0.0 : k, lz = (row == (N >> 1)) ? 0.0 : l;
-                    // (-i lz + i*(i kz)) * x = (-kz - i lz) * x
-                    x = make_double2(-kz * x.x + lz * x.y, -kz * x.y - lz * x.x);
-                } break;
-                default: break;
-            }
-        }
+// spectral multiplier of the prologue modes at (row, col) applied to x
+template <int N, int PRO>
+__device__ __forceinline__ cd fft_prologue_one(const FftArgs& a, int row, int col, cd x) {
+    const double k = a.dk * (double)sidx(col, N), l = a.dk * (double)sidx(row, N);
+    if (PRO == PRO_IK) return make_double2(-k * x.y, k * x.x);
+    if (PRO == PRO_IL) return make_double2(-l * x.y, l * x.x);
+    if (PRO == PRO_NEG_WV2) { const double w = -(k * k + l * l); return make_double2(w * x.x, w * x.y); }
+    if (PRO == PRO_WV4) { double w = k * k + l * l; w = w * w; return make_double2(w * x.x, w * x.y); }
+    if (PRO == PRO_UV) {
+        const double kz = (col == (N >> 1)) ? 0.0 : k, lz = (row == (N >> 1)) ? 0.0 : l;
+        // (-i lz + i*(i kz)) * x = (-kz - i lz) * x
+        return make_double2(-kz * x.x + lz * x.y, -kz * x.y - lz * x.x);
     }
-    if (a.conj_in) x.y = -x.y;
     return x;
 }
 
 template <int N>
 __device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int row, int col, cd x) {
     const size_t idx = mbase + (size_t)row * N + col;
-    if (a.conj_out) x.y = -x.y;
     x.x *= a.scale;
-    x.y *= a.scale;
+    x.y *= a.scale_im;            // = -scale when the output is conjugated
     if (a.epi == EPI_REAL_OUT) ((double*)a.out)[idx] = x.x;
     else ((cd*)a.out)[idx] = x;
 }
@@ -104,7 +92,8 @@ template <int M, int W, int C, bool COL> struct Tile {
     static constexpr int TPF = M / fftc::E;      // threads per local transform
     static constexpr int T = W * TPF;            // threads per CTA
     static constexpr int LINE = fftc::phys_len(M);
-    static constexpr size_t SMEM = (size_t)W * LINE * sizeof(cd);
+    static constexpr int TWLEN = fftc::tw_table_len(M) + 1;           // stage twiddles, copied to shared memory
+    static constexpr size_t SMEM = ((size_t)W * LINE + TWLEN) * sizeof(cd);
     static constexpr int MINB = (T <= 256) ? 2 : 1;   // resident CTAs per SM the register budget is cut for
     __device__ static __forceinline__ int slot(int w, int o) {
         return COL ? fftc::phys(o) * W + w : w * LINE + fftc::phys(o);
@@ -112,30 +101,33 @@ template <int M, int W, int C, bool COL> struct Tile {
 };
 
 // what happens to the result of the last local stage
-template <int M, int W, int C, bool COL>
+template <int M, int W, int C, bool COL, bool DIF>
 __device__ __forceinline__ void fft_emit(const FftArgs& a, size_t mbase, int line, int w, int c, int k, cd x, cd* smem) {
     using TL = Tile<M, W, C, COL>;
     if constexpr (C == 1) {
         fft_store<TL::N>(a, mbase, COL ? k : line, COL ? line : k, x);
+    } else if constexpr (DIF) {
+        const int n = C * k + c;    // decimation in frequency: CTA c produced the outputs congruent to c mod C
+        fft_store<TL::N>(a, mbase, COL ? n : line, COL ? line : n, x);
     } else {
         smem[TL::slot(w, k)] = x;   // E_c[k]; the cluster twiddle w_N^{c k} is applied by the gathering CTA
     }
 }
 
-template <int M, int W, int C, bool COL, int NS>
-__device__ __forceinline__ void fft_stages(cd (&v)[fftc::E], int j, int w, int c, cd* smem, const FftArgs& a,
-                                           int line, size_t mbase) {
+template <int M, int W, int C, bool COL, bool DIF, int NS>
+__device__ __forceinline__ void fft_stages(cd (&v)[fftc::E], int j, int w, int c, cd* smem, const cd* tw,
+                                           const FftArgs& a, int line, size_t mbase) {
     using TL = Tile<M, W, C, COL>;
     constexpr int R = fftc::StageRadix<M, NS>::R;
     constexpr int S = fftc::E / R;
     constexpr bool LAST = (NS * R == M);
-    fftc::stage_compute<M, NS>(v, j, a.tw);
+    fftc::stage_compute<M, NS>(v, j, tw);
     if (LAST) {
 #pragma unroll
         for (int u = 0; u < S; ++u)
 #pragma unroll
             for (int p = 0; p < R; ++p)
-                fft_emit<M, W, C, COL>(a, mbase, line, w, c, fftc::stage_out_index<M, NS>(j, u, p), v[u + p * S], smem);
+                fft_emit<M, W, C, COL, DIF>(a, mbase, line, w, c, fftc::stage_out_index<M, NS>(j, u, p), v[u + p * S], smem);
     } else {
 #pragma unroll
         for (int u = 0; u < S; ++u)
@@ -145,7 +137,7 @@ __device__ __forceinline__ void fft_stages(cd (&v)[fftc::E], int j, int w, int c
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) v[e] = smem[TL::slot(w, j + e * TL::TPF)];
         __syncthreads();
-        fft_stages<M, W, C, COL, LAST ? NS : NS * R>(v, j, w, c, smem, a, line, mbase);
+        fft_stages<M, W, C, COL, DIF, LAST ? NS : NS * R>(v, j, w, c, smem, tw, a, line, mbase);
     }
 }
 
@@ -194,14 +186,52 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     const int group = blockIdx.x / C;
     const int line = group * W + w;
     const size_t mbase = (size_t)blockIdx.y * N * N;
+    // stage twiddles -> shared memory: L1 is invalidated by every cluster-scope acquire on this SM, and a global
+    // twiddle load sits on the critical path of every stage
+    cd* smtw = smem + (size_t)W * TL::LINE;
+    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
     cd v[fftc::E];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
+    // all 16 loads are issued back to back (nothing between them depends on loaded data); the prologue multiply and
+    // the conjugation of an inverse transform run afterwards, behind ONE uniform branch
+    if (a.pro == PRO_REAL_IN) {
+        const double* in = (const double*)a.in + mbase;
 #pragma unroll
-    for (int e = 0; e < fftc::E; ++e) {
-        const int n = C * (j + e * TL::TPF) + c;           // decimated sub-sequence of CTA c
-        v[e] = fft_load<N>(a, mbase, COL ? n : line, COL ? line : n);
+        for (int e = 0; e < fftc::E; ++e) {
+            const int n = C * (j + e * TL::TPF) + c;       // decimated sub-sequence of CTA c
+            v[e] = make_double2(in[COL ? (size_t)n * N + line : (size_t)line * N + n], 0.0);
+        }
+    } else {
+        const cd* in = (const cd*)a.in + mbase;
+#pragma unroll
+        for (int e = 0; e < fftc::E; ++e) {
+            const int n = C * (j + e * TL::TPF) + c;
+            v[e] = in[COL ? (size_t)n * N + line : (size_t)line * N + n];
+        }
     }
-    fft_stages<M, W, C, COL, 1>(v, j, w, c, smem, a, line, mbase);
+#define NIWQG_PRO_CASE(P)                                                                     \
+    case P:                                                                                   \
+        _Pragma("unroll") for (int e = 0; e < fftc::E; ++e) {                                 \
+            const int n = C * (j + e * TL::TPF) + c;                                          \
+            v[e] = fft_prologue_one<N, P>(a, COL ? n : line, COL ? line : n, v[e]);           \
+        }                                                                                     \
+        break;
+    if (a.pro > PRO_REAL_IN) {
+        switch (a.pro) {
+            NIWQG_PRO_CASE(PRO_IK)
+            NIWQG_PRO_CASE(PRO_IL)
+            NIWQG_PRO_CASE(PRO_NEG_WV2)
+            NIWQG_PRO_CASE(PRO_WV4)
+            NIWQG_PRO_CASE(PRO_UV)
+            default: break;
+        }
+    }
+#undef NIWQG_PRO_CASE
+    if (a.conj_in) {
+#pragma unroll
+        for (int e = 0; e < fftc::E; ++e) v[e].y = -v[e].y;
+    }
+    fft_stages<M, W, C, COL, false, 1>(v, j, w, c, smem, smtw, a, line, mbase);
     if constexpr (C > 1) {
         // radix-C butterfly across the cluster: this CTA owns k in [c M/C, (c+1) M/C) of every line of the group
         cg::cluster_group cluster = cg::this_cluster();
@@ -249,6 +279,120 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster split, decimation in FREQUENCY with PUSHES (the default for C > 1):
+//   CTA c loads x[m + M r], r = 0..C-1, for its m in [c M/C, (c+1) M/C) (whole 64 B row segments in the column
+//   pass, two contiguous chunks in the row pass), runs the radix-C butterfly, multiplies Y_q[m] by w_N^{m q} and
+//   STORES it into CTA q's shared memory (st.shared::cluster: fire and forget, nobody waits for a remote load).
+//   After ONE cluster barrier CTA q holds its whole sub-sequence Y_q[0..M) and transforms it locally:
+//   X[C k + q] = FFT_M(Y_q)[k].  No CTA touches a peer's memory after the barrier, so no exit barrier is needed.
+template <int M, int W, int C, bool COL>
+__global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pass_dif(FftArgs a) {
+    using TL = Tile<M, W, C, COL>;
+    constexpr int N = TL::N;
+    static_assert(C > 1 && C <= 8, "cluster sizes 2, 4, 8");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd* smem = reinterpret_cast<cd*>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x;
+    int w, j;
+    if (COL) { w = tid % W; j = tid / W; } else { j = tid % TL::TPF; w = tid / TL::TPF; }
+    const int c = (int)(blockIdx.x % C);
+    const int group = blockIdx.x / C;
+    const int line = group * W + w;
+    const size_t mbase = (size_t)blockIdx.y * N * N;
+    cd* smtw = smem + (size_t)W * TL::LINE;
+    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+    fft_prefetch<M, W, C, COL>(a, group, c, tid);
+    constexpr int PPT = fftc::E / C;                        // radix-C butterflies per thread
+    cd v[fftc::E];
+    // butterfly i of this thread: line wq of the group, sub-sequence index m; its inputs are x[m + M r]
+#define NIWQG_BF(i)                                                        \
+    const int g_ = tid + (i) * TL::T;                                      \
+    const int wq = COL ? g_ % W : 0;                                       \
+    const int m = c * (M / C) + (COL ? g_ / W : g_);                       \
+    const int ln = group * W + wq;
+    if (a.pro == PRO_REAL_IN) {
+        const double* in = (const double*)a.in + mbase;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            NIWQG_BF(i)
+#pragma unroll
+            for (int r = 0; r < C; ++r) {
+                const int n = m + M * r;
+                v[i * C + r] = make_double2(in[COL ? (size_t)n * N + ln : (size_t)ln * N + n], 0.0);
+            }
+        }
+    } else {
+        const cd* in = (const cd*)a.in + mbase;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            NIWQG_BF(i)
+#pragma unroll
+            for (int r = 0; r < C; ++r) {
+                const int n = m + M * r;
+                v[i * C + r] = in[COL ? (size_t)n * N + ln : (size_t)ln * N + n];
+            }
+        }
+    }
+    cd wk[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        NIWQG_BF(i)
+        wk[i] = a.twc[m];                                   // w_N^m
+        (void)wq; (void)ln;
+    }
+#define NIWQG_PRO_CASE(P)                                                                         \
+    case P:                                                                                       \
+        _Pragma("unroll") for (int i = 0; i < PPT; ++i) {                                         \
+            NIWQG_BF(i)                                                                           \
+            _Pragma("unroll") for (int r = 0; r < C; ++r) {                                       \
+                const int n = m + M * r;                                                          \
+                v[i * C + r] = fft_prologue_one<N, P>(a, COL ? n : ln, COL ? ln : n, v[i * C + r]); \
+            }                                                                                     \
+        }                                                                                         \
+        break;
+    if (a.pro > PRO_REAL_IN) {
+        switch (a.pro) {
+            NIWQG_PRO_CASE(PRO_IK)
+            NIWQG_PRO_CASE(PRO_IL)
+            NIWQG_PRO_CASE(PRO_NEG_WV2)
+            NIWQG_PRO_CASE(PRO_WV4)
+            NIWQG_PRO_CASE(PRO_UV)
+            default: break;
+        }
+    }
+#undef NIWQG_PRO_CASE
+    if (a.conj_in) {
+#pragma unroll
+        for (int e = 0; e < fftc::E; ++e) v[e].y = -v[e].y;
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        NIWQG_BF(i)
+        (void)ln;
+        fftc::dft<C, 1>(v + i * C);
+        cd pw[C];                                           // w_N^{m q}, q = 0..C-1
+        pw[0] = make_double2(1.0, 0.0);
+        pw[1] = wk[i];
+#pragma unroll
+        for (int q = 2; q < C; ++q) pw[q] = cmul(pw[q >> 1], pw[q - (q >> 1)]);
+#pragma unroll
+        for (int p = 0; p < C; ++p) {
+            const int q = fftc::outidx<C>(p);
+            cd* dst = cluster.map_shared_rank(smem, q);
+            dst[TL::slot(wq, m)] = (q == 0) ? v[i * C + p] : cmul(v[i * C + p], pw[q]);
+        }
+    }
+#undef NIWQG_BF
+    cluster_arrive_release();
+    cluster_wait_acquire();
+#pragma unroll
+    for (int e = 0; e < fftc::E; ++e) v[e] = smem[TL::slot(w, j + e * TL::TPF)];
+    __syncthreads();
+    fft_stages<M, W, C, COL, true, 1>(v, j, w, c, smem, smtw, a, line, mbase);
+}
+
 // ---- pass geometry: (M, W, C) per grid size
 template <int N, bool COL> struct PassCfg {
     // column pass: W = 4 adjacent columns (64 B per row access), 1024-point local transforms for N >= 1024
@@ -267,6 +411,10 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(k_fft_pass<M, W, C, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)TL::SMEM);
         if (e != cudaSuccess) return e;
+        if constexpr (C > 1) {
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+            if (e != cudaSuccess) return e;
+        }
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -283,6 +431,9 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     cfg.numAttrs = (C > 1) ? 1 : 0;
     FftArgs b = a;
     b.pf_groups = (a.pf_groups > 0 && (N / W) * C > 2 * a.pf_groups) ? (a.pf_groups + C - 1) / C : 0;   // CTAs -> groups
+    if constexpr (C > 1) {
+        if (!(a.variant & (COL ? 1 : 2))) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL>, b);
+    }
     return cudaLaunchKernelEx(&cfg, k_fft_pass<M, W, C, COL>, b);
 }
 

@@ -61,6 +61,7 @@ struct niwqg_handle {
     // reductions
     double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *scal = nullptr, *stagev = nullptr;
     bool q_set = false, phi_set = false;
+    int fft_variant = 2;        // FftArgs::variant: column clusters push (DIF), row clusters pull (DIT) - measured best
     int pf_ctas = 296;          // L2 prefetch distance of the FFT passes in CTAs (~ one resident wave: 148 SMs x 2)
     // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg)
     bool prof = false;
@@ -125,14 +126,16 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     a.twc = h->twc;
     a.dk = h->dk;
     a.pf_groups = h->pf_ctas;
+    a.variant = h->fft_variant;
     // pass 1: rows
     a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row;
-    a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0;
+    a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
     { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
     // pass 2: columns
     a.in = out; a.out = (epi == EPI_REAL_OUT) ? real_out : (void*)out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col;
     a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
     a.scale = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
+    a.scale_im = inverse ? -a.scale : a.scale;
     { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, batch, h->stream)); }
     h->launches += 2;
     return 0;
@@ -443,6 +446,7 @@ static int create_impl(niwqg_handle* h) {
     const int N = p.nx;
     CK(cudaSetDevice(p.device));
     if (const char* e = getenv("NIWQG_PF_CTAS")) h->pf_ctas = atoi(e);   // tuning knob (0 = no prefetch)
+    if (const char* e = getenv("NIWQG_FFT_VARIANT")) h->fft_variant = atoi(e);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
