@@ -40,6 +40,12 @@ typedef struct niwqg_params {
     int use_filter, dealias;
     int passive_scalar;         /* QGModel only                                  */
     double nu4c, nuc, muc;      /* QGModel passive scalar                        */
+    /* slab decomposition of ONE grid over nranks GPUs (one process per GPU); 0 or 1 = single GPU.
+     * Physical arrays passed to set_q / set_phi and returned by get_field are then the rank's rows
+     * [rank*nx/nranks, (rank+1)*nx/nranks); spectral arrays are (nx, nx/nranks) column slabs in the
+     * conjugate-symmetric ownership described in csrc/common.cuh (struct Grid). */
+    int rank, nranks;
+    char nccl_id[128];          /* ncclUniqueId from niwqg_nccl_unique_id() on rank 0, shared by the caller */
 } niwqg_params;
 
 typedef struct niwqg_handle niwqg_handle;
@@ -133,12 +139,16 @@ int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind);
 #define NIWQG_JAC_PSI_PHI  2
 int niwqg_jacobian(niwqg_handle* h, int which, void* out);
 
+/* rank 0: a fresh ncclUniqueId (128 bytes) for niwqg_params.nccl_id; the caller broadcasts it (e.g. with
+ * torch.distributed).  NCCL is dlopen()ed from $NIWQG_NCCL_LIB or the default search path. */
+int niwqg_nccl_unique_id(char* out128);
+
 int niwqg_sync(niwqg_handle* h);
 /* CUDA-event timing on the handle's stream: elapsed ms of `nsteps` steps */
 int niwqg_time_steps(niwqg_handle* h, int nsteps, float* ms);
 /* per-kernel-kind CUDA-event timing on the handle's stream.  Reads the records accumulated since the
- * last call into ms_out[5] / count_out[5] (kinds: 0 FFT row pass, 1 FFT column pass, 2 physical-space
- * pointwise, 3 spectral pointwise, 4 small reductions), clears them and switches recording on/off.
+ * last call into ms_out[6] / count_out[6] (kinds: 0 FFT row pass, 1 FFT column pass, 2 physical-space
+ * pointwise, 3 spectral pointwise, 4 small reductions, 5 NCCL all-to-all of slab transforms), clears them and switches recording on/off.
  * ms_out/count_out may be NULL. */
 int niwqg_profile(niwqg_handle* h, int enable, double* ms_out, long long* count_out);
 /* number of kernel launches issued by this handle so far */

@@ -44,6 +44,9 @@ class Kernel(object):
     Parameters are those of niwqg/Kernel.py:70-98 (SI units), plus
         batch  : number of independent ensemble members stepped together (default 1)
         device : CUDA device ordinal (default 0)
+        rank, nranks, nccl_id : slab decomposition of ONE grid over nranks GPUs (one process per GPU;
+                 see niwqg_b200/slab.py).  set_q/set_phi then take the whole-grid array (each rank keeps its
+                 rows) or the rank's rows; physical attributes return the rank's rows.
     ``use_mkl`` / ``nthreads`` are accepted and ignored (the FFT backend is the CUDA engine).
     """
 
@@ -64,7 +67,8 @@ class Kernel(object):
     def __init__(self, nx=128, ny=None, L=5e5, dt=10000., twrite=1000., tmax=250000., use_filter=True,
                  cflmax=0.8, U=.0, f=1.e-4, N=0.01, m=0.025, g=9.81, nu4=0, nu4w=0, nu=20, nuw=50., mu=0, muw=0,
                  dealias=False, save_to_disk=False, overwrite=True, tsave_snapshots=10, tdiags=10,
-                 path='output/', use_mkl=False, nthreads=1, batch=1, device=0):
+                 path='output/', use_mkl=False, nthreads=1, batch=1, device=0, rank=0, nranks=1,
+                 nccl_id=None):
         self.nx = nx
         self.ny = nx                    # niwqg/Kernel.py:100-103: ny is ignored (F9)
         self.L = L
@@ -91,6 +95,8 @@ class Kernel(object):
         self.nthreads = nthreads
         self.batch = batch
         self.device = device
+        # slab decomposition of this grid over nranks GPUs, one process per GPU (niwqg_b200/slab.py builds these)
+        self.rank, self.nranks, self._nccl_id = rank, nranks, nccl_id
 
         self._initialize_logger()
         self.logger.info(self.model)
@@ -108,7 +114,9 @@ class Kernel(object):
                              L=self.L, dt=self.dt, U=self.U, f=self.f, N=self.N, m=self.m,
                              nu=self.nu, nu4=self.nu4, mu=self.mu, nuw=self.nuw, nu4w=self.nu4w, muw=self.muw,
                              beta=0.0, use_filter=int(bool(self.use_filter)), dealias=int(bool(self.dealias)),
-                             passive_scalar=0, nu4c=0.0, nuc=0.0, muc=0.0)
+                             passive_scalar=0, nu4c=0.0, nuc=0.0, muc=0.0,
+                             **({} if self.nranks <= 1 else dict(rank=self.rank, nranks=self.nranks,
+                                                                  nccl_id=self._nccl_id)))
         if self.use_filter:
             self.logger.info(' Using filter')
         elif self.dealias:

@@ -36,7 +36,7 @@ JAC_PSI_Q, JAC_PHIC_PHI, JAC_PSI_PHI = range(3)
 EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "niwqg_set_phi", "niwqg_set_c",
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
-           "niwqg_launch_count", "niwqg_stream", "niwqg_profile"]
+           "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id"]
 
 
 class Params(C.Structure):
@@ -45,7 +45,8 @@ class Params(C.Structure):
                 ("m", C.c_double), ("nu", C.c_double), ("nu4", C.c_double), ("mu", C.c_double),
                 ("nuw", C.c_double), ("nu4w", C.c_double), ("muw", C.c_double), ("beta", C.c_double),
                 ("use_filter", C.c_int), ("dealias", C.c_int), ("passive_scalar", C.c_int),
-                ("nu4c", C.c_double), ("nuc", C.c_double), ("muc", C.c_double)]
+                ("nu4c", C.c_double), ("nuc", C.c_double), ("muc", C.c_double),
+                ("rank", C.c_int), ("nranks", C.c_int), ("nccl_id", C.c_ubyte * 128)]
 
 
 _lib = None
@@ -81,18 +82,80 @@ def load():
     lib.niwqg_profile.argtypes = [vp, ip, vp, vp]
     lib.niwqg_stream.argtypes = [vp]
     lib.niwqg_stream.restype = vp
+    lib.niwqg_nccl_unique_id.argtypes = [vp]
     _lib = lib
     return lib
+
+
+def _nccl_library_path():
+    """The NCCL that ships with torch (site-packages/nvidia/nccl/lib); None = leave it to the dynamic loader."""
+    if os.environ.get("NIWQG_NCCL_LIB"):
+        return os.environ["NIWQG_NCCL_LIB"]
+    try:
+        import nvidia.nccl as _n
+        for d in list(_n.__path__):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId (call on rank 0, broadcast to the other ranks, pass as nccl_id=...)."""
+    path = _nccl_library_path()
+    if path:
+        os.environ["NIWQG_NCCL_LIB"] = path
+    lib = load()
+    buf = C.create_string_buffer(128)
+    rc = lib.niwqg_nccl_unique_id(buf)
+    if rc != 0:
+        msg = lib.niwqg_last_error(None)
+        raise RuntimeError("niwqg_nccl_unique_id failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+    return buf.raw
+
+
+# ---- slab column map (mirror of struct Grid in csrc/common.cuh); pure Python so that CPU tests can check it
+def slab_kx(N, nranks, rank):
+    """Global column index kx of every local spectral column of `rank` (length N/nranks)."""
+    if nranks == 1:
+        return np.arange(N)
+    h = N // (2 * nranks)
+    lc = np.arange(2 * h)
+    kx = np.where(lc < h, rank * h + lc, N - (rank * h + lc - h))
+    if rank == 0:
+        kx[h] = N // 2
+    return kx
+
+
+def slab_owner(N, nranks, kx):
+    """(rank, local column) that holds global column kx."""
+    h = N // (2 * nranks)
+    if kx < N // 2:
+        return kx // h, kx % h
+    if kx == N // 2:
+        return 0, h
+    m = N - kx
+    return m // h, h + m % h
 
 
 class Handle(object):
     """Owns one niwqg_handle.  Every method raises RuntimeError on a non-zero return."""
 
     def __init__(self, **kw):
+        path = _nccl_library_path() if kw.get("nranks", 1) > 1 else None
+        if path:
+            os.environ["NIWQG_NCCL_LIB"] = path
         self.lib = load()
         p = Params()
         for k, v in kw.items():
-            setattr(p, k, v)
+            if k == "nccl_id":      # raw 128 bytes (a c_char array would stop at the first NUL)
+                if v is None or len(v) != 128:
+                    raise ValueError("nccl_id must be the 128 bytes of nccl_unique_id()")
+                C.memmove(C.addressof(p) + Params.nccl_id.offset, bytes(v), 128)
+            else:
+                setattr(p, k, v)
         self.params = p
         self.h = C.c_void_p()
         rc = self.lib.niwqg_create(C.byref(p), C.byref(self.h))
@@ -101,7 +164,9 @@ class Handle(object):
             self.h = None
             raise RuntimeError("niwqg_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
         self.N, self.B = p.nx, p.batch
-        self.nk = p.nx // 2 + 1 if p.model == MODEL_QG else p.nx
+        self.nranks, self.rank = max(1, p.nranks), (p.rank if p.nranks > 1 else 0)
+        self.nyl = p.nx // self.nranks            # local physical rows
+        self.nk = p.nx // 2 + 1 if p.model == MODEL_QG else p.nx // self.nranks   # local spectral columns
 
     def _ck(self, rc):
         if rc != 0:
@@ -122,7 +187,9 @@ class Handle(object):
     # -- seeding -----------------------------------------------------------
     def _host(self, a, dtype):
         a = np.ascontiguousarray(a, dtype=dtype)
-        want = self.B * self.N * self.N
+        if self.nranks > 1 and a.size == self.N * self.N:      # whole-grid array: keep this rank's rows
+            a = np.ascontiguousarray(a.reshape(self.N, self.N)[self.rank * self.nyl:(self.rank + 1) * self.nyl])
+        want = self.B * self.nyl * self.N
         if a.size != want:
             if a.size == self.N * self.N and self.B > 1:
                 a = np.ascontiguousarray(np.broadcast_to(a.reshape(1, self.N, self.N), (self.B, self.N, self.N)))
@@ -163,12 +230,12 @@ class Handle(object):
     def sync(self):
         self._ck(self.lib.niwqg_sync(self.h))
 
-    PROFILE_KINDS = ("fft_row", "fft_col", "phys", "spec", "small")
+    PROFILE_KINDS = ("fft_row", "fft_col", "phys", "spec", "small", "comm")
 
     def profile(self, enable):
         """Switch per-kernel-kind event timing on/off; returns {kind: (total_ms, launches)} recorded so far."""
-        ms = np.zeros(5)
-        cnt = np.zeros(5, np.int64)
+        ms = np.zeros(len(self.PROFILE_KINDS))
+        cnt = np.zeros(len(self.PROFILE_KINDS), np.int64)
         self._ck(self.lib.niwqg_profile(self.h, int(bool(enable)), ms.ctypes.data, cnt.ctypes.data))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 
@@ -196,9 +263,9 @@ class Handle(object):
         fid = F[name]
         N, nk = self.N, self.nk
         if name in REAL_FIELDS:
-            shape, dt = ((N, nk) if name == "FILTR" else (N, N)), np.float64
+            shape, dt = ((N, nk) if name == "FILTR" else (self.nyl, N)), np.float64
         elif name in PHYS_CPLX_FIELDS:
-            shape, dt = (N, N), np.complex128
+            shape, dt = (self.nyl, N), np.complex128
         else:
             shape, dt = (N, nk), np.complex128
         members = [0] if (name in TABLE_FIELDS) else (range(self.B) if member is None else [member])
@@ -227,7 +294,14 @@ class Handle(object):
         else:
             a = np.ascontiguousarray(x, np.complex128)
             out = np.empty((N, N), np.complex128)
-        if kind != FFT_C2R and a.shape != (N, N):
+        if self.nranks > 1:
+            # slab: forward takes this rank's rows (nyl, N) and returns its column slab (N, ncl); inverse the reverse
+            fwd = kind in (FFT_C2C_FWD, FFT_R2C_FULL)
+            want = (self.nyl, N) if fwd else (N, self.nk)
+            if a.shape != want:
+                raise ValueError("slab fft input must be %s" % (want,))
+            out = np.empty((N, self.nk) if fwd else (self.nyl, N), np.complex128)
+        elif kind != FFT_C2R and a.shape != (N, N):
             raise ValueError("fft input must be (%d,%d)" % (N, N))
         self._ck(self.lib.niwqg_fft2(self.h, a.ctypes.data, out.ctypes.data, kind))
         return out

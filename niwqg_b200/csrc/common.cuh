@@ -9,6 +9,38 @@
 // signed wavenumber index of the kernel-family grid: [0..N/2-1, -N/2..-1]  (niwqg/Kernel.py:242-244)
 __host__ __device__ __forceinline__ int sidx(int i, int N) { return i < (N >> 1) ? i : i - N; }
 
+// Spectral-array geometry.  Natural layout (one GPU): [N rows ky][N columns kx].  Slab layout (P ranks): every
+// rank holds all N rows of ncl = N/P columns, chosen so that column kx and its conjugate partner N-kx live on the
+// same rank (the (K,-K) pair kernels stay local): local columns [0,h) are kx = rank*h + lc, local columns [h,2h)
+// are their mirrors N - (rank*h + lc - h); rank 0, whose first column kx=0 is its own mirror, holds the Nyquist
+// column N/2 (also its own mirror) in slot h instead.
+struct Grid {
+    int N;          // global grid edge
+    double dk;      // 2 pi / L
+    int ncl;        // local spectral columns (N when not decomposed)
+    int h;          // ncl / 2
+    int rank;       // slab rank
+    int sym;        // 1 = slab layout, 0 = natural
+};
+__host__ __device__ __forceinline__ int grid_kx(const Grid& g, int lc) {
+    if (!g.sym) return lc;
+    if (lc < g.h) return g.rank * g.h + lc;
+    if (g.rank == 0 && lc == g.h) return g.N >> 1;
+    return g.N - (g.rank * g.h + lc - g.h);
+}
+__host__ __device__ __forceinline__ int grid_partner(const Grid& g, int lc) {
+    if (!g.sym) return (g.N - lc) & (g.N - 1);
+    if (g.rank == 0 && (lc == 0 || lc == g.h)) return lc;
+    return lc < g.h ? lc + g.h : lc - g.h;
+}
+// owner rank and local column of global column kx in the slab layout over P ranks (h = N / (2 P))
+__host__ __device__ __forceinline__ void grid_owner(int N, int h, int kx, int& rank, int& lc) {
+    const int H = N >> 1;
+    if (kx < H) { rank = kx / h; lc = kx % h; }
+    else if (kx == H) { rank = 0; lc = h; }
+    else { const int m = N - kx; rank = m / h; lc = h + m % h; }
+}
+
 // Deterministic block reduction of K partial sums; block result lands in partials[blockIdx.x*K + k].
 template <int K>
 __device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partials) {

@@ -58,8 +58,32 @@ struct FftArgs {
     double scale, scale_im;   // output multipliers of the real / imaginary part (scale_im = -scale: conjugate)
     double dk;
     int pf_groups;    // L2 prefetch distance in line groups (0 = off)
+    // geometry: natural [lines][N] arrays unless stated otherwise
+    Grid g;           // spectral column map (prologue wavenumbers, exchange layout)
+    int nlines;       // lines transformed by this pass: rows (row pass) or local columns (column pass)
+    int pitch;        // column pass: elements between consecutive rows (N, or ncl in the slab layout)
+    int xmap_in, xmap_out;   // row pass of a slab transform: load / store through the all-to-all exchange layout
+    int xchunk;       // exchange layout: elements per peer chunk (nyl * ncl)
+    size_t mstride;   // elements between ensemble members
     int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel
 };
+
+// element n of line `line`: offset inside one member's array
+//   column pass: n-th row of local column `line`;  row pass: natural [line][n], or - on the exchange side of a slab
+//   transform - [owner(n)][line][lc(n)] (the layout ncclAlltoAll moves between the row slabs and the column slabs)
+template <int N, bool COL>
+__device__ __forceinline__ size_t fft_index(const FftArgs& a, int xmap, int line, int n) {
+    if (COL) return (size_t)n * a.pitch + line;
+    if (!xmap) return (size_t)line * N + n;
+    int r, lc;
+    grid_owner(N, a.g.h, n, r, lc);
+    return (size_t)r * a.xchunk + (size_t)line * a.g.ncl + lc;
+}
+// (ky, kx) of element n of line `line` on the spectral side (prologue wavenumbers)
+template <bool COL>
+__device__ __forceinline__ void fft_kykx(const FftArgs& a, int line, int n, int& ky, int& kx) {
+    if (COL) { ky = n; kx = grid_kx(a.g, line); } else { ky = line; kx = n; }
+}
 
 // spectral multiplier of the prologue modes at (row, col) applied to x
 template <int N, int PRO>
@@ -77,9 +101,9 @@ __device__ __forceinline__ cd fft_prologue_one(const FftArgs& a, int row, int co
     return x;
 }
 
-template <int N>
-__device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int row, int col, cd x) {
-    const size_t idx = mbase + (size_t)row * N + col;
+template <int N, bool COL>
+__device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int line, int n, cd x) {
+    const size_t idx = mbase + fft_index<N, COL>(a, a.xmap_out, line, n);
     x.x *= a.scale;
     x.y *= a.scale_im;            // = -scale when the output is conjugated
     if (a.epi == EPI_REAL_OUT) ((double*)a.out)[idx] = x.x;
@@ -105,10 +129,10 @@ template <int M, int W, int C, bool COL, bool DIF>
 __device__ __forceinline__ void fft_emit(const FftArgs& a, size_t mbase, int line, int w, int c, int k, cd x, cd* smem) {
     using TL = Tile<M, W, C, COL>;
     if constexpr (C == 1) {
-        fft_store<TL::N>(a, mbase, COL ? k : line, COL ? line : k, x);
+        fft_store<TL::N, COL>(a, mbase, line, k, x);
     } else if constexpr (DIF) {
         const int n = C * k + c;    // decimation in frequency: CTA c produced the outputs congruent to c mod C
-        fft_store<TL::N>(a, mbase, COL ? n : line, COL ? line : n, x);
+        fft_store<TL::N, COL>(a, mbase, line, n, x);
     } else {
         smem[TL::slot(w, k)] = x;   // E_c[k]; the cluster twiddle w_N^{c k} is applied by the gathering CTA
     }
@@ -158,9 +182,9 @@ __device__ __forceinline__ void fft_prefetch(const FftArgs& a, int group, int c,
     using TL = Tile<M, W, C, COL>;
     constexpr int N = TL::N;
     const int g = group + a.pf_groups;
-    if (COL || a.pf_groups <= 0 || g >= N / W) return;   // column pass: the per-row requests cost more L1 wavefronts than they save
+    if (COL || a.xmap_in || a.pf_groups <= 0 || g >= a.nlines / W) return;   // column pass: the per-row requests cost more L1 wavefronts than they save
     const size_t esz = (a.pro == PRO_REAL_IN) ? sizeof(double) : sizeof(cd);
-    const char* base = (const char*)a.in + (size_t)blockIdx.y * N * N * esz;
+    const char* base = (const char*)a.in + (size_t)blockIdx.y * a.mstride * esz;
     if (COL) {
         // rows C m + c, columns [g W, g W + W): one line-sized request per row
         for (int m = tid; m < M; m += TL::T) prefetch_l2(base + ((size_t)(C * m + c) * N + (size_t)g * W) * esz);
@@ -185,7 +209,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     const int c = (C > 1) ? (int)(blockIdx.x % C) : 0;     // rank in the (C,1,1) cluster
     const int group = blockIdx.x / C;
     const int line = group * W + w;
-    const size_t mbase = (size_t)blockIdx.y * N * N;
+    const size_t mbase = (size_t)blockIdx.y * a.mstride;
     // stage twiddles -> shared memory: L1 is invalidated by every cluster-scope acquire on this SM, and a global
     // twiddle load sits on the critical path of every stage
     cd* smtw = smem + (size_t)W * TL::LINE;
@@ -199,21 +223,23 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) {
             const int n = C * (j + e * TL::TPF) + c;       // decimated sub-sequence of CTA c
-            v[e] = make_double2(in[COL ? (size_t)n * N + line : (size_t)line * N + n], 0.0);
+            v[e] = make_double2(in[fft_index<N, COL>(a, a.xmap_in, line, n)], 0.0);
         }
     } else {
         const cd* in = (const cd*)a.in + mbase;
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) {
             const int n = C * (j + e * TL::TPF) + c;
-            v[e] = in[COL ? (size_t)n * N + line : (size_t)line * N + n];
+            v[e] = in[fft_index<N, COL>(a, a.xmap_in, line, n)];
         }
     }
 #define NIWQG_PRO_CASE(P)                                                                     \
     case P:                                                                                   \
         _Pragma("unroll") for (int e = 0; e < fftc::E; ++e) {                                 \
             const int n = C * (j + e * TL::TPF) + c;                                          \
-            v[e] = fft_prologue_one<N, P>(a, COL ? n : line, COL ? line : n, v[e]);           \
+            int ky_, kx_;                                                                     \
+            fft_kykx<COL>(a, line, n, ky_, kx_);                                              \
+            v[e] = fft_prologue_one<N, P>(a, ky_, kx_, v[e]);                                 \
         }                                                                                     \
         break;
     if (a.pro > PRO_REAL_IN) {
@@ -272,7 +298,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
             for (int p = 0; p < C; ++p) {
                 const int n = k + M * fftc::outidx<C>(p);
-                fft_store<N>(a, mbase, COL ? n : ln, COL ? ln : n, v[i * C + p]);
+                fft_store<N, COL>(a, mbase, ln, n, v[i * C + p]);
             }
         }
         cluster_wait_relaxed();     // nobody may exit while a peer still reads its shared memory
@@ -300,7 +326,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     const int c = (int)(blockIdx.x % C);
     const int group = blockIdx.x / C;
     const int line = group * W + w;
-    const size_t mbase = (size_t)blockIdx.y * N * N;
+    const size_t mbase = (size_t)blockIdx.y * a.mstride;
     cd* smtw = smem + (size_t)W * TL::LINE;
     for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
             for (int r = 0; r < C; ++r) {
                 const int n = m + M * r;
-                v[i * C + r] = make_double2(in[COL ? (size_t)n * N + ln : (size_t)ln * N + n], 0.0);
+                v[i * C + r] = make_double2(in[fft_index<N, COL>(a, a.xmap_in, ln, n)], 0.0);
             }
         }
     } else {
@@ -331,7 +357,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
             for (int r = 0; r < C; ++r) {
                 const int n = m + M * r;
-                v[i * C + r] = in[COL ? (size_t)n * N + ln : (size_t)ln * N + n];
+                v[i * C + r] = in[fft_index<N, COL>(a, a.xmap_in, ln, n)];
             }
         }
     }
@@ -348,7 +374,9 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
             NIWQG_BF(i)                                                                           \
             _Pragma("unroll") for (int r = 0; r < C; ++r) {                                       \
                 const int n = m + M * r;                                                          \
-                v[i * C + r] = fft_prologue_one<N, P>(a, COL ? n : ln, COL ? ln : n, v[i * C + r]); \
+                int ky_, kx_;                                                                     \
+                fft_kykx<COL>(a, ln, n, ky_, kx_);                                                \
+                v[i * C + r] = fft_prologue_one<N, P>(a, ky_, kx_, v[i * C + r]);                 \
             }                                                                                     \
         }                                                                                         \
         break;
@@ -418,7 +446,7 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((N / W) * C, batch, 1);
+    cfg.gridDim = dim3((a.nlines / W) * C, batch, 1);
     cfg.blockDim = dim3(TL::T, 1, 1);
     cfg.dynamicSmemBytes = TL::SMEM;
     cfg.stream = st;
@@ -430,7 +458,8 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     cfg.attrs = at;
     cfg.numAttrs = (C > 1) ? 1 : 0;
     FftArgs b = a;
-    b.pf_groups = (a.pf_groups > 0 && (N / W) * C > 2 * a.pf_groups) ? (a.pf_groups + C - 1) / C : 0;   // CTAs -> groups
+    if (a.nlines % W) return cudaErrorInvalidValue;
+    b.pf_groups = (a.pf_groups > 0 && (a.nlines / W) * C > 2 * a.pf_groups) ? (a.pf_groups + C - 1) / C : 0;   // CTAs -> groups
     if constexpr (C > 1) {
         if (!(a.variant & (COL ? 1 : 2))) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL>, b);
     }

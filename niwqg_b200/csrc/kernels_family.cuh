@@ -20,10 +20,7 @@ enum {
     MF_SKIP_P2   = 1 << 7,   // [D] first half of a QL stage: P1 + sums only
 };
 
-struct Grid {
-    int N;          // grid edge
-    double dk;      // 2 pi / L
-};
+// Grid (N, dk, local spectral columns, slab ownership) and the column maps grid_kx / grid_partner: common.cuh
 
 // ======================================================================
 // ETDRK4 tables + filter (Kernel.py:267-284, :400-454; YBJModel.py:89-121)
@@ -75,7 +72,8 @@ __device__ void etdrk4_point(cd ch, double dt, cd& E, cd& E2, cd& Q, cd& f0, cd&
 struct TableSet { cd *E, *E2, *Q, *f0, *fab, *fc; };
 
 struct InitArgs {
-    int N, nk;               // nk = N (c2c) or N/2+1 (QG half spectrum)
+    Grid g;                  // slab column map (kernel family); g.sym == 0 for the natural layout
+    int N, nk;               // nk = local spectral columns: N (c2c), N/P (slab) or N/2+1 (QG half spectrum)
     int half;                // 1: QG wavenumber convention (k = dk*col, col<=N/2)
     double dk, dt, dx;
     double U;
@@ -91,7 +89,7 @@ __global__ void k_init_tables(InitArgs a) {
     const size_t total = (size_t)a.N * a.nk;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / a.nk), col = (int)(i % a.nk);
-        const double k = a.dk * (double)(a.half ? col : sidx(col, a.N));
+        const double k = a.dk * (double)(a.half ? col : sidx(grid_kx(a.g, col), a.N));
         const double l = a.dk * (double)sidx(row, a.N);
         const double wv2 = __dadd_rn(__dmul_rn(k, k), __dmul_rn(l, l));
         const double wv4 = __dmul_rn(wv2, wv2);
@@ -108,8 +106,8 @@ __global__ void k_init_tables(InitArgs a) {
                 const double wvx = sqrt((k * a.dx) * (k * a.dx) + (l * a.dx) * (l * a.dx));
                 if (wvx > cphi) { const double d = wvx - cphi; fl = exp(-23.6 * (d * d) * (d * d)); }
             } else if (a.dealias) {
-                const int lo = a.N / 3, hi = 2 * a.N / 3;
-                if ((row >= lo && row < hi) || (col >= lo && col < hi)) fl = 0.0;
+                const int lo = a.N / 3, hi = 2 * a.N / 3, kxi = a.half ? col : grid_kx(a.g, col);
+                if ((row >= lo && row < hi) || (kxi >= lo && kxi < hi)) fl = 0.0;
             }
             a.filtr[i] = fl;
         }
@@ -170,14 +168,15 @@ __device__ __forceinline__ void pack_uv_general(double k1, double l1, double k2,
 }
 
 __global__ void k_spec_invert(InvertArgs a) {
-    const int N = a.g.N, H = N >> 1;
-    const size_t npts = (size_t)N * N, mb = (size_t)blockIdx.y * npts;
-    const size_t total = (size_t)(H + 1) * N;
+    const int N = a.g.N, H = N >> 1, NC = a.g.ncl;
+    const size_t npts = (size_t)N * NC, mb = (size_t)blockIdx.y * npts;
+    const size_t total = (size_t)(H + 1) * NC;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int ky = (int)(t / N), kx = (int)(t % N);
-        const int kyp = (N - ky) & (N - 1), kxp = (N - kx) & (N - 1);
-        if (kyp == ky && kx > H) continue;
-        const size_t i1 = mb + (size_t)ky * N + kx, i2 = mb + (size_t)kyp * N + kxp;
+        const int ky = (int)(t / NC), lc = (int)(t % NC);
+        const int kyp = (N - ky) & (N - 1), lcp = grid_partner(a.g, lc);
+        if (kyp == ky && lcp < lc) continue;              // each (K, -K) pair once
+        const int kx = grid_kx(a.g, lc), kxp = grid_kx(a.g, lcp);
+        const size_t i1 = mb + (size_t)ky * NC + lc, i2 = mb + (size_t)kyp * NC + lcp;
         const bool self = (i1 == i2);
         const double k1 = a.g.dk * (double)sidx(kx, N), l1 = a.g.dk * (double)sidx(ky, N);
         const double k2 = a.g.dk * (double)sidx(kxp, N), l2 = a.g.dk * (double)sidx(kyp, N);
@@ -201,7 +200,7 @@ __global__ void k_spec_invert(InvertArgs a) {
             const cd A = make_double2(0.5 * (W1.x + W2.x), 0.5 * (W1.y - W2.y));     // fft(|phi|^2)(K)
             cd Jc = make_double2(a.inv_jscale * 0.5 * (W1.y + W2.y), a.inv_jscale * -0.5 * (W1.x - W2.x));   // -0.5i (W1 - conj W2)
             if (ky == 0 && kx == 0) Jc = make_double2(0.0, 0.0);
-            const double fl = a.filtr[(size_t)ky * N + kx];
+            const double fl = a.filtr[(size_t)ky * NC + lc];
             qw.x = 0.5 * (0.5 * (-wv2 * A.x) + Jc.x) / a.f * fl;
             qw.y = 0.5 * (0.5 * (-wv2 * A.y) + Jc.y) / a.f * fl;
         }
@@ -221,14 +220,15 @@ __global__ void k_spec_invert(InvertArgs a) {
 // QL wave advection velocity (QLModel.py:65-66): packed spectrum of Re ifft(-il ph_q) + i Re ifft(ik ph_q),
 // ph_q = -wv2i*qh, from whatever qh is current when jacobian_psi_phi is called.
 __global__ void k_spec_uvq(Grid g, const cd* __restrict__ qh, cd* __restrict__ uvq) {
-    const int N = g.N, H = N >> 1;
-    const size_t npts = (size_t)N * N, mb = (size_t)blockIdx.y * npts;
-    const size_t total = (size_t)(H + 1) * N;
+    const int N = g.N, H = N >> 1, NC = g.ncl;
+    const size_t npts = (size_t)N * NC, mb = (size_t)blockIdx.y * npts;
+    const size_t total = (size_t)(H + 1) * NC;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int ky = (int)(t / N), kx = (int)(t % N);
-        const int kyp = (N - ky) & (N - 1), kxp = (N - kx) & (N - 1);
-        if (kyp == ky && kx > H) continue;
-        const size_t i1 = mb + (size_t)ky * N + kx, i2 = mb + (size_t)kyp * N + kxp;
+        const int ky = (int)(t / NC), lc = (int)(t % NC);
+        const int kyp = (N - ky) & (N - 1), lcp = grid_partner(g, lc);
+        if (kyp == ky && lcp < lc) continue;
+        const int kx = grid_kx(g, lc), kxp = grid_kx(g, lcp);
+        const size_t i1 = mb + (size_t)ky * NC + lc, i2 = mb + (size_t)kyp * NC + lcp;
         const double k1 = g.dk * (double)sidx(kx, N), l1 = g.dk * (double)sidx(ky, N);
         const double k2 = g.dk * (double)sidx(kxp, N), l2 = g.dk * (double)sidx(kyp, N);
         const double wv2 = __dadd_rn(__dmul_rn(k1, k1), __dmul_rn(l1, l1));
@@ -372,18 +372,20 @@ __device__ __forceinline__ cd etd_update(int stage, cd y0, cd y1, cd Fn, cd& F0,
 }
 
 __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
-    const int N = a.g.N, H = N >> 1;
-    const size_t npts = (size_t)N * N, mb = (size_t)blockIdx.y * npts;
-    const size_t total = (size_t)(H + 1) * N;
+    const int N = a.g.N, H = N >> 1, NC = a.g.ncl;
+    const size_t npts = (size_t)N * NC, mb = (size_t)blockIdx.y * npts;
+    const size_t total = (size_t)(H + 1) * NC;
     const int st = a.stage;
     double s[SE_COUNT];
 #pragma unroll
     for (int k = 0; k < SE_COUNT; ++k) s[k] = 0.0;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int ky = (int)(t / N), kx = (int)(t % N);
-        const int kyp = (N - ky) & (N - 1), kxp = (N - kx) & (N - 1);
-        if (kyp == ky && kx > H) continue;
-        const size_t t1 = (size_t)ky * N + kx, t2 = (size_t)kyp * N + kxp;   // table indices
+        const int ky = (int)(t / NC), lc = (int)(t % NC);
+        const int kyp = (N - ky) & (N - 1), lcp = grid_partner(a.g, lc);
+        if (kyp == ky && lcp < lc) continue;
+        const int kx = grid_kx(a.g, lc), kxp = grid_kx(a.g, lcp);
+        const size_t t1 = (size_t)ky * NC + lc, t2 = (size_t)kyp * NC + lcp;   // table indices
+        const bool mode00 = (ky == 0 && kx == 0);
         const size_t i1 = mb + t1, i2 = mb + t2;
         const bool self = (t1 == t2);
         const double fl1 = a.filtr[t1], fl2 = a.filtr[t2];
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
         // ---------------- phi equation
         if (a.do_phi) {
             cd F1 = a.P2[i1], F2 = a.P2[i2];
-            if ((a.flags & MF_FIX00) && t1 == 0) {
+            if ((a.flags & MF_FIX00) && mode00) {
                 const double* sd = a.sumsD + (size_t)blockIdx.y * SD_COUNT;
                 F1.x += sd[SD_J_R]; F1.y += sd[SD_J_I];
                 F2 = F1;
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
             // jach(K) = i k A + i l B ; jach(-K) = i k2 conj(A) + i l2 conj(B);  Fn = -jach
             cd F1 = make_double2(k1 * A.y + l1 * B.y, -(k1 * A.x + l1 * B.x));
             cd F2 = make_double2(-(k2 * A.y + l2 * B.y), -(k2 * A.x + l2 * B.x));
-            if (t1 == 0) { F1 = make_double2(0.0, 0.0); F2 = F1; }
+            if (mode00) { F1 = make_double2(0.0, 0.0); F2 = F1; }
             const cd cur1 = (st == 1) ? a.y0q[i1] : a.yq[i1];
             const cd cur2 = (st == 1) ? a.y0q[i2] : a.yq[i2];
             {   // budget sums on the pre-update state
@@ -495,14 +497,14 @@ struct SpecSumArgs {
 };
 
 __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_sums(SpecSumArgs a, double* partials) {
-    const int N = a.g.N;
-    const size_t npts = (size_t)N * N, mb = (size_t)blockIdx.y * npts;
+    const int N = a.g.N, NC = a.g.ncl;
+    const size_t npts = (size_t)N * NC, mb = (size_t)blockIdx.y * npts;
     double s[SS_COUNT];
 #pragma unroll
     for (int k = 0; k < SS_COUNT; ++k) s[k] = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += (size_t)gridDim.x * blockDim.x) {
-        if (i == 0) continue;
-        const int ky = (int)(i / N), kx = (int)(i % N);
+        const int ky = (int)(i / NC), kx = grid_kx(a.g, (int)(i % NC));
+        if (ky == 0 && kx == 0) continue;
         const double k = a.g.dk * (double)sidx(kx, N), l = a.g.dk * (double)sidx(ky, N);
         const double wv2 = k * k + l * l, wv2i = 1.0 / wv2;
         const cd ph = a.ph[mb + i], qh = a.qh[mb + i];

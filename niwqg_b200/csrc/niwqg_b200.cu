@@ -10,6 +10,8 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "../../include/niwqg_b200.h"
 #include "fft2d.cuh"
 #include "kernels_family.cuh"
@@ -61,6 +63,14 @@ struct niwqg_handle {
     // reductions
     double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *scal = nullptr, *stagev = nullptr;
     bool q_set = false, phi_set = false;
+    // slab decomposition over nranks GPUs (one process per GPU): physical arrays hold nyl = N/P rows, spectral
+    // arrays all N rows of ncl = N/P columns (Grid, common.cuh); each 2-D transform = local pass, NCCL all-to-all,
+    // local pass
+    int rank = 0, nranks = 1, nyl = 0, ncl = 0;
+    Grid g{};
+    double Mg = 0;              // N*N of the GLOBAL grid (mean denominators)
+    cd *X = nullptr, *Y = nullptr;   // all-to-all send / receive buffers
+    ncclComm_t comm = nullptr;
     int fft_variant = 2;        // FftArgs::variant: column clusters push (DIF), row clusters pull (DIT) - measured best
     int pf_ctas = 296;          // L2 prefetch distance of the FFT passes in CTAs (~ one resident wave: 148 SMs x 2)
     // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg)
@@ -71,7 +81,7 @@ struct niwqg_handle {
     size_t prof_used = 0;
 };
 
-enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COUNT };
+enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_COUNT };
 
 static cudaEvent_t prof_event(niwqg_handle* h) {
     if (h->prof_used == h->prof_pool.size()) {
@@ -119,24 +129,115 @@ static void build_twiddles(int N, std::vector<cd>& tw) {
     }
 }
 
-// 2-D c2c transform of `batch` members: in -> out (may alias), forward or inverse
-static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro, int batch, int epi = EPI_NONE,
-                void* real_out = nullptr) {
-    FftArgs a{};
+// ---- NCCL, resolved at run time so that single-GPU use needs no NCCL at all
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(std::string& err) {
+    if (g_nccl.lib) return 0;
+    const char* path = getenv("NIWQG_NCCL_LIB");
+    void* lib = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return -4; }
+#define NIWQG_SYM(field, name)                                                     \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                                   \
+    if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return -4; }
+    NIWQG_SYM(GetUniqueId, "ncclGetUniqueId") NIWQG_SYM(CommInitRank, "ncclCommInitRank")
+    NIWQG_SYM(CommDestroy, "ncclCommDestroy") NIWQG_SYM(AllReduce, "ncclAllReduce") NIWQG_SYM(Send, "ncclSend")
+    NIWQG_SYM(Recv, "ncclRecv") NIWQG_SYM(GroupStart, "ncclGroupStart") NIWQG_SYM(GroupEnd, "ncclGroupEnd")
+    NIWQG_SYM(GetErrorString, "ncclGetErrorString")
+#undef NIWQG_SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t e__ = (call);                                                                 \
+        if (e__ != ncclSuccess) {                                                                  \
+            char buf__[512];                                                                       \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(e__)); \
+            h->err = buf__;                                                                        \
+            return -5;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+// the distributed-FFT transpose: chunk s of `send` goes to rank s, chunk r of `recv` comes from rank r
+static int slab_all_to_all(niwqg_handle* h, const cd* send, cd* recv) {
+    PROF(PK_COMM);
+    const size_t chunk = (size_t)h->nyl * h->ncl;
+    NK(g_nccl.GroupStart());
+    for (int r = 0; r < h->nranks; ++r) {
+        NK(g_nccl.Send(send + (size_t)r * chunk, 2 * chunk, ncclDouble, r, h->comm, h->stream));
+        NK(g_nccl.Recv(recv + (size_t)r * chunk, 2 * chunk, ncclDouble, r, h->comm, h->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    return 0;
+}
+
+static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.twc = h->twc;
     a.dk = h->dk;
     a.pf_groups = h->pf_ctas;
     a.variant = h->fft_variant;
-    // pass 1: rows
-    a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row;
-    a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
-    { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
-    // pass 2: columns
-    a.in = out; a.out = (epi == EPI_REAL_OUT) ? real_out : (void*)out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col;
-    a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
-    a.scale = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
-    a.scale_im = inverse ? -a.scale : a.scale;
-    { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, batch, h->stream)); }
+    a.g = h->g;
+    a.xmap_in = a.xmap_out = 0;
+    a.xchunk = h->nyl * h->ncl;
+    a.mstride = h->npts;
+    a.pitch = h->ncl;
+}
+
+// 2-D c2c transform of `batch` members: in -> out (may alias), forward or inverse.
+// One GPU: row pass then column pass.  Slab: forward = row pass (rows are local) -> all-to-all -> column pass
+// (columns are local); inverse = column pass -> all-to-all -> row pass.  The spectral prologue multiply and the
+// conjugation of an inverse transform ride on whichever pass comes first, conj + 1/N^2 on the last.
+static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro, int batch, int epi = EPI_NONE,
+                void* real_out = nullptr) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    const double sc = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
+    void* final_out = (epi == EPI_REAL_OUT) ? real_out : (void*)out;
+    if (h->nranks == 1) {
+        // pass 1: rows
+        a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->N;
+        a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+        { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
+        // pass 2: columns
+        a.in = out; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col; a.nlines = h->N;
+        a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
+        a.scale = sc; a.scale_im = inverse ? -sc : sc;
+        { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, batch, h->stream)); }
+        h->launches += 2;
+        return 0;
+    }
+    if (batch != 1) { h->err = "slab transforms take one member"; return -1; }
+    if (!inverse) {
+        a.in = in; a.out = h->X; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_out = 1;
+        a.conj_in = 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+        { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+        int r = slab_all_to_all(h, h->X, h->Y);
+        if (r) return r;
+        a.in = h->Y; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col; a.nlines = h->ncl; a.xmap_out = 0;
+        { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
+    } else {
+        a.in = in; a.out = h->X; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_col; a.nlines = h->ncl;
+        a.conj_in = 1; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+        { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
+        int r = slab_all_to_all(h, h->X, h->Y);
+        if (r) return r;
+        a.in = h->Y; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1;
+        a.conj_in = 0; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
+        { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+    }
     h->launches += 2;
     return 0;
 }
@@ -151,6 +252,8 @@ static int finalize(niwqg_handle* h, int K, double* out, int is_max = 0) {
     k_finalize<<<h->B, 32, 0, h->stream>>>(h->part, NIWQG_PW_BLOCKS, K, out, is_max);
     CK(cudaGetLastError());
     h->launches += 1;
+    if (h->nranks > 1)   // every rank reduced its slab; the grid-wide sum / max is the same on all ranks afterwards
+        NK(g_nccl.AllReduce(out, out, (size_t)h->B * K, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
     return 0;
 }
 #define FIN(...)                              \
@@ -195,7 +298,7 @@ __global__ void k_budget(BudgetArgs a) {
 
 static BudgetArgs budget_args(niwqg_handle* h, int stage) {
     BudgetArgs b{};
-    b.stage = stage; b.M = (double)h->npts; b.f = h->p.f; b.hslash = h->hslash; b.kappa2 = h->kappa2; b.dt = h->p.dt;
+    b.stage = stage; b.M = h->Mg; b.f = h->p.f; b.hslash = h->hslash; b.kappa2 = h->kappa2; b.dt = h->p.dt;
     b.nu4 = h->p.nu4; b.nu = h->p.nu; b.mu = h->p.mu; b.nu4w = h->p.nu4w; b.nuw = h->p.nuw; b.muw = h->p.muw;
     b.sumsD = h->sumsD; b.sumsE = h->sumsE; b.scal = h->scal; b.stagev = h->stagev;
     return b;
@@ -222,7 +325,7 @@ static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
 // _invert + _calc_rel_vorticity + (u,v) for the current (qh, phi, phix, phiy)
 static int invert_family(niwqg_handle* h) {
     InvertArgs ia{};
-    ia.g = Grid{h->N, h->dk};
+    ia.g = h->g;
     ia.flags = h->flags; ia.f = h->p.f; ia.qh = h->qh[h->cq]; ia.filtr = h->filtr;
     ia.ph = h->ph; ia.qs = h->qs;
     if (h->flags & MF_WAVE_PV) {
@@ -256,7 +359,7 @@ static PhysArgs phys_args(niwqg_handle* h, int extra_flags) {
 }
 
 static int ql_wave_velocity(niwqg_handle* h) {   // uq, vq from the current qh (QLModel.py:65-66)
-    { PROF(PK_SPEC); k_spec_uvq<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(Grid{h->N, h->dk}, h->qh[h->cq], h->uvq); }
+    { PROF(PK_SPEC); k_spec_uvq<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->g, h->qh[h->cq], h->uvq); }
     CK(cudaGetLastError());
     h->launches++;
     FFT(h->uvq, h->uvq, true, PRO_NONE, h->B);
@@ -274,7 +377,7 @@ static int step_family(niwqg_handle* h) {
             FFT(cur, h->phiy, true, PRO_IL, h->B);
         }
         StageArgs sa{};
-        sa.g = Grid{h->N, h->dk};
+        sa.g = h->g;
         sa.stage = st; sa.flags = h->flags; sa.do_q = ybj ? 0 : 1; sa.do_phi = 1;
         sa.P1 = h->P1; sa.P2 = h->P2;
         sa.y0q = h->qh[oq]; sa.y0p = h->phih[op]; sa.yq = h->qh[nq]; sa.yp = h->phih[np];
@@ -392,7 +495,7 @@ static int step_qg(niwqg_handle* h) {
         if (st == 1) { h->cq = nq; h->cc = nc; }
         FIN(QE_COUNT, h->sumsE);
         QgBudgetArgs ba{};
-        ba.stage = st; ba.M = (double)h->npts; ba.dt = h->p.dt; ba.nu4 = h->p.nu4; ba.nu = h->p.nu; ba.mu = h->p.mu;
+        ba.stage = st; ba.M = h->Mg; ba.dt = h->p.dt; ba.nu4 = h->p.nu4; ba.nu = h->p.nu; ba.mu = h->p.mu;
         ba.nu4c = h->p.nu4c; ba.muc = h->p.muc; ba.ps = ps ? 1 : 0;
         ba.sumsE = h->sumsE; ba.scal = h->scal; ba.stagev = h->stagev;
         { PROF(PK_SMALL); k_qg_budget<<<h->B, 32, 0, h->stream>>>(ba); }
@@ -432,6 +535,7 @@ int niwqg_destroy(niwqg_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -451,8 +555,20 @@ static int create_impl(niwqg_handle* h) {
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     h->N = N; h->B = p.batch; h->model = p.model; h->qg = (p.model == NIWQG_MODEL_QG);
-    h->nk = h->qg ? N / 2 + 1 : N;
-    h->npts = (size_t)N * N; h->nspec = (size_t)N * h->nk;
+    h->nranks = p.nranks > 1 ? p.nranks : 1;
+    h->rank = h->nranks > 1 ? p.rank : 0;
+    h->nyl = N / h->nranks; h->ncl = N / h->nranks;
+    h->nk = h->qg ? N / 2 + 1 : h->ncl;
+    h->npts = (size_t)h->nyl * N; h->nspec = (size_t)N * h->nk;
+    h->Mg = (double)N * (double)N;
+    h->g = Grid{N, 2.0 * M_PI / p.L, h->ncl, h->ncl / 2, h->rank, h->nranks > 1 ? 1 : 0};
+    if (h->nranks > 1) {
+        int r = nccl_load(h->err);
+        if (r) return r;
+        ncclUniqueId id;
+        memcpy(&id, p.nccl_id, sizeof id);
+        NK(g_nccl.CommInitRank(&h->comm, h->nranks, id, h->rank));
+    }
     h->dk = 2.0 * M_PI / p.L; h->dx = p.L / N;
     {   // power of two nearest 1/k_mid^2, k_mid = dk*N/8 (scaling of the packed wave-PV transform)
         const double kmid = h->dk * N / 8.0;
@@ -501,7 +617,7 @@ static int create_impl(niwqg_handle* h) {
     };
     DA(h->filtr, h->nspec * sizeof(double));
     InitArgs ia{};
-    ia.N = N; ia.nk = h->nk; ia.half = h->qg ? 1 : 0; ia.dk = h->dk; ia.dt = p.dt; ia.dx = h->dx; ia.U = p.U;
+    ia.g = h->g; ia.N = N; ia.nk = h->nk; ia.half = h->qg ? 1 : 0; ia.dk = h->dk; ia.dt = p.dt; ia.dx = h->dx; ia.U = p.U;
     ia.use_filter = p.use_filter; ia.dealias = p.dealias;
     bool filtr_done = false;
     if (p.model != NIWQG_MODEL_YBJ) {
@@ -528,6 +644,7 @@ static int create_impl(niwqg_handle* h) {
     DA(h->qh[0], ssz); DA(h->ph, ssz); DA(h->uv, fsz); DA(h->qs, fsz);
     DA(h->P1, fsz); DA(h->P2, fsz); DA(h->W, fsz);
     DA(h->rscratch, B * h->npts * sizeof(double));
+    if (h->nranks > 1) { DA(h->X, fsz); DA(h->Y, fsz); }
     if (p.model != NIWQG_MODEL_YBJ) { DA(h->qh[1], ssz); DA(h->y1q, ssz); DA(h->F0q, ssz); DA(h->Fabq, ssz); }
     if (!h->qg) {
         DA(h->phih[0], ssz); DA(h->phih[1], ssz); DA(h->y1p, ssz); DA(h->F0p, ssz); DA(h->Fabp, ssz);
@@ -552,6 +669,12 @@ int niwqg_create(const niwqg_params* p, niwqg_handle** out) {
     if (N < 32 || N > 8192 || (N & (N - 1))) { g_create_error = "nx must be a power of two in [32, 8192]"; return -1; }
     if (p->batch < 1) { g_create_error = "batch must be >= 1"; return -1; }
     if (p->model < NIWQG_MODEL_QG || p->model > NIWQG_MODEL_QL) { g_create_error = "unknown model"; return -1; }
+    if (p->nranks > 1) {
+        const int P = p->nranks;
+        if ((P & (P - 1)) || N / P < 16 || p->rank < 0 || p->rank >= P) { g_create_error = "slab: nranks must be a power of two with nx/nranks >= 16, 0 <= rank < nranks"; return -1; }
+        if (p->model == NIWQG_MODEL_QG) { g_create_error = "slab: QGModel (half spectrum) is single-GPU only"; return -1; }
+        if (p->batch != 1) { g_create_error = "slab: batch must be 1 (ensembles shard whole members per GPU instead)"; return -1; }
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         g_create_error = "no CUDA device: niwqg_b200 has no CPU fallback";
@@ -565,6 +688,16 @@ int niwqg_create(const niwqg_params* p, niwqg_handle** out) {
     return 0;
 }
 
+int niwqg_nccl_unique_id(char* out128) {
+    std::string err;
+    int r = nccl_load(err);
+    if (r) { g_create_error = err; return r; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return -5; }
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
 int niwqg_sync(niwqg_handle* h) {
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -575,7 +708,7 @@ void* niwqg_stream(const niwqg_handle* h) { return (void*)h->stream; }
 
 static int ke_qg_family(niwqg_handle* h) {   // 0.5*spec_var(wv*ph) (Kernel.py:600-602) -> sumsX via k_spec_sums
     SpecSumArgs sa{};
-    sa.g = Grid{h->N, h->dk}; sa.ph = h->ph; sa.qh = h->qh[h->cq]; sa.qwh = h->qwh;
+    sa.g = h->g; sa.ph = h->ph; sa.qh = h->qh[h->cq]; sa.qwh = h->qwh;
     sa.phih = (h->flags & MF_HAS_LAP2) ? h->phih[h->cp] : nullptr;
     k_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
     CK(cudaGetLastError());
@@ -594,7 +727,7 @@ int niwqg_set_q(niwqg_handle* h, const double* q, int on_device) {
     const size_t n = (size_t)h->B * h->npts;
     CK(cudaMemcpyAsync(h->rscratch, q, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                        h->stream));
-    const double M2 = (double)h->npts * (double)h->npts;
+    const double M2 = h->Mg * h->Mg;
     if (h->qg) {
         // qh = rfft2(q): full c2c of the real field, keep columns 0..N/2 (QGModel.py:516-518)
         FFT(h->rscratch, h->W, false, PRO_REAL_IN, h->B);
@@ -670,7 +803,7 @@ int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
     FFT(h->phi, h->phih[h->cp], false, PRO_NONE, h->B);
     int r = pe_niw_refresh(h, h->sumsX);
     if (r) return r;
-    const double M = (double)h->npts;
+    const double M = h->Mg;
     k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_PW, h->sumsX, 1, 0, 0.25 / M / h->kappa2);
     CK(cudaGetLastError());
     k_phi2_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->npts, h->part);
@@ -700,7 +833,7 @@ int niwqg_set_c(niwqg_handle* h, const double* c, int on_device) {
     k_qg_spec_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa, h->part);
     CK(cudaGetLastError());
     FIN(QS_COUNT, h->sumsX);
-    const double M2 = (double)h->npts * (double)h->npts;
+    const double M2 = h->Mg * h->Mg;
     k_set_scalar_from_sum<<<h->B, 32, 0, h->stream>>>(h->scal, NIWQG_S_CVAR, h->sumsX, QS_COUNT, QS_C2, 1.0 / M2);
     CK(cudaGetLastError());
     h->launches += 3;
@@ -765,7 +898,7 @@ int niwqg_get_scalars(niwqg_handle* h, double* out) {
 int niwqg_status(niwqg_handle* h, double* out) {
     CK(cudaSetDevice(h->p.device));
     std::vector<double> sx((size_t)h->B * 16), tmp((size_t)h->B * 16);
-    const double M = (double)h->npts, M2 = M * M;
+    const double M = h->Mg, M2 = M * M;
     if (h->qg) {
         // ke_qg and cfl from the current (qh, ph): u, v are refreshed from ph (QGModel.py:571-629)
         int r = qg_expand_and_invert(h, h->qh[h->cq]);
@@ -818,7 +951,7 @@ int niwqg_status(niwqg_handle* h, double* out) {
 int niwqg_diagnostics(niwqg_handle* h, double* out) {
     CK(cudaSetDevice(h->p.device));
     const int B = h->B;
-    const double M = (double)h->npts, M2 = M * M;
+    const double M = h->Mg, M2 = M * M;
     std::vector<double> sc((size_t)B * NIWQG_S_COUNT), sd((size_t)B * 16), ss((size_t)B * 16), sg((size_t)B), s3((size_t)B * 3),
         sq((size_t)B);
     if (h->qg) {
@@ -1029,6 +1162,7 @@ int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
     CK(cudaSetDevice(h->p.device));
     const size_t c = h->npts * sizeof(cd), r = h->npts * sizeof(double);
     const int N = h->N, nh = N / 2 + 1;
+    if (h->nranks > 1 && (kind == NIWQG_FFT_R2C || kind == NIWQG_FFT_C2R)) { h->err = "fft2: half-spectrum kinds are single-GPU only"; return -1; }
     switch (kind) {
         case NIWQG_FFT_C2C_FWD:
         case NIWQG_FFT_C2C_INV:
@@ -1065,6 +1199,7 @@ int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
 int niwqg_jacobian(niwqg_handle* h, int which, void* out) {
     CK(cudaSetDevice(h->p.device));
     if (h->B != 1) { h->err = "jacobian: batch==1 only"; return -1; }
+    if (h->nranks > 1) { h->err = "jacobian: single-GPU layout only"; return -1; }
     if (h->qg) {
         if (which != NIWQG_JAC_PSI_Q) { h->err = "jacobian: QGModel has J(psi,q) only"; return -1; }
         int r = qg_expand_and_invert(h, h->qh[h->cq]);
