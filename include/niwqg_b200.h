@@ -143,6 +143,13 @@ int niwqg_jacobian(niwqg_handle* h, int which, void* out);
  * torch.distributed).  NCCL is dlopen()ed from $NIWQG_NCCL_LIB or the default search path. */
 int niwqg_nccl_unique_id(char* out128);
 
+/* Fused slab exchange over NVLink peer memory: every rank exports the CUDA-IPC handles of its two receive buffers
+ * (out: 2 x 64 bytes), the caller all-gathers them, and niwqg_ipc_import() maps the peers' buffers; from then on the
+ * first pass of every slab transform stores straight into the owners' buffers instead of going through ncclSend/Recv.
+ * Without these calls the NCCL all-to-all path is used. */
+int niwqg_ipc_export(niwqg_handle* h, char* out, size_t bytes);
+int niwqg_ipc_import(niwqg_handle* h, const char* all_ranks, size_t bytes_per_rank);
+
 int niwqg_sync(niwqg_handle* h);
 /* CUDA-event timing on the handle's stream: elapsed ms of `nsteps` steps */
 int niwqg_time_steps(niwqg_handle* h, int nsteps, float* ms);

@@ -36,7 +36,8 @@ JAC_PSI_Q, JAC_PHIC_PHI, JAC_PSI_PHI = range(3)
 EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "niwqg_set_phi", "niwqg_set_c",
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
-           "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id"]
+           "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id",
+           "niwqg_ipc_export", "niwqg_ipc_import"]
 
 
 class Params(C.Structure):
@@ -83,6 +84,8 @@ def load():
     lib.niwqg_stream.argtypes = [vp]
     lib.niwqg_stream.restype = vp
     lib.niwqg_nccl_unique_id.argtypes = [vp]
+    lib.niwqg_ipc_export.argtypes = [vp, vp, C.c_size_t]
+    lib.niwqg_ipc_import.argtypes = [vp, vp, C.c_size_t]
     _lib = lib
     return lib
 
@@ -183,6 +186,19 @@ class Handle(object):
             self.close()
         except Exception:
             pass
+
+    # -- slab: fused exchange over peer memory ------------------------------
+    IPC_BYTES = 128
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(self.IPC_BYTES)
+        self._ck(self.lib.niwqg_ipc_export(self.h, buf, self.IPC_BYTES))
+        return buf.raw
+
+    def ipc_import(self, all_ranks_bytes):
+        if len(all_ranks_bytes) != self.IPC_BYTES * self.nranks:
+            raise ValueError("expected %d bytes of IPC handles" % (self.IPC_BYTES * self.nranks))
+        self._ck(self.lib.niwqg_ipc_import(self.h, all_ranks_bytes, self.IPC_BYTES))
 
     # -- seeding -----------------------------------------------------------
     def _host(self, a, dtype):

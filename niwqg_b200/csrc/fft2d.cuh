@@ -64,6 +64,9 @@ struct FftArgs {
     int pitch;        // column pass: elements between consecutive rows (N, or ncl in the slab layout)
     int xmap_in, xmap_out;   // row pass of a slab transform: load / store through the all-to-all exchange layout
     int xchunk;       // exchange layout: elements per peer chunk (nyl * ncl)
+    int push;         // slab: the pass's stores go straight into the owners' receive buffers over NVLink (peer[])
+    int nyl_shift;    // log2(rows per rank)
+    cd* peer[8];      // receive buffer of every rank (peer[rank] = own), CUDA-IPC mapped
     size_t mstride;   // elements between ensemble members
     int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel
 };
@@ -103,9 +106,25 @@ __device__ __forceinline__ cd fft_prologue_one(const FftArgs& a, int row, int co
 
 template <int N, bool COL>
 __device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int line, int n, cd x) {
-    const size_t idx = mbase + fft_index<N, COL>(a, a.xmap_out, line, n);
     x.x *= a.scale;
     x.y *= a.scale_im;            // = -scale when the output is conjugated
+    if (a.push) {
+        // the all-to-all of a slab transform fused into this pass: the element lands in its owner's receive buffer,
+        // chunk [my rank][row within the owner's slab][local column] - exactly what ncclAlltoAll would deliver
+        int r;
+        size_t off;
+        if (COL) {               // inverse transform, column pass: row n belongs to rank n / nyl
+            r = n >> a.nyl_shift;
+            off = (size_t)(n - (r << a.nyl_shift)) * a.g.ncl + line;
+        } else {                 // forward transform, row pass: column n belongs to owner(n)
+            int lc;
+            grid_owner(N, a.g.h, n, r, lc);
+            off = (size_t)line * a.g.ncl + lc;
+        }
+        a.peer[r][(size_t)a.g.rank * a.xchunk + off] = x;
+        return;
+    }
+    const size_t idx = mbase + fft_index<N, COL>(a, a.xmap_out, line, n);
     if (a.epi == EPI_REAL_OUT) ((double*)a.out)[idx] = x.x;
     else ((cd*)a.out)[idx] = x;
 }

@@ -69,7 +69,13 @@ struct niwqg_handle {
     int rank = 0, nranks = 1, nyl = 0, ncl = 0;
     Grid g{};
     double Mg = 0;              // N*N of the GLOBAL grid (mean denominators)
-    cd *X = nullptr, *Y = nullptr;   // all-to-all send / receive buffers
+    cd *X = nullptr, *Y = nullptr;   // all-to-all send / receive buffers (NCCL path)
+    // fused path: passes push straight into the peers' receive buffers (CUDA IPC), double-buffered per transform
+    cd* Yp[2] = {nullptr, nullptr};
+    cd* peerY[2][8] = {};
+    bool p2p = false;
+    int ybuf = 0;
+    double* bar = nullptr;      // 1-element all-reduce buffer: the cross-GPU barrier between the two passes
     ncclComm_t comm = nullptr;
     int fft_variant = 2;        // FftArgs::variant: column clusters push (DIF), row clusters pull (DIT) - measured best
     int pf_ctas = 296;          // L2 prefetch distance of the FFT passes in CTAs (~ one resident wave: 148 SMs x 2)
@@ -220,6 +226,37 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         return 0;
     }
     if (batch != 1) { h->err = "slab transforms take one member"; return -1; }
+    if (h->p2p) {
+        // fused exchange: the first pass stores into the owners' receive buffers over NVLink; one tiny all-reduce is
+        // the barrier that says "everybody's pushes have landed"; the second pass reads the local receive buffer.
+        const int b = h->ybuf;
+        h->ybuf ^= 1;     // the peers may still be reading the other buffer (previous transform's second pass)
+        a.push = 1;
+        for (int r = 0; r < h->nranks; ++r) a.peer[r] = h->peerY[b][r];
+        int sh = 0;
+        while ((1 << sh) < h->nyl) ++sh;
+        a.nyl_shift = sh;
+        a.in = in; a.out = nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0; a.conj_out = 0;
+        if (!inverse) {
+            a.tw = h->tw_row; a.nlines = h->nyl; a.conj_in = 0;
+            { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+        } else {
+            a.tw = h->tw_col; a.nlines = h->ncl; a.conj_in = 1;
+            { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
+        }
+        { PROF(PK_COMM); NK(g_nccl.AllReduce(h->bar, h->bar, 1, ncclDouble, ncclSum, h->comm, h->stream)); }
+        a.push = 0;
+        a.in = h->Yp[b]; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.conj_in = 0;
+        if (!inverse) {
+            a.tw = h->tw_col; a.nlines = h->ncl;
+            { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
+        } else {
+            a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
+            { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+        }
+        h->launches += 3;
+        return 0;
+    }
     if (!inverse) {
         a.in = in; a.out = h->X; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_out = 1;
         a.conj_in = 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
@@ -535,6 +572,10 @@ int niwqg_destroy(niwqg_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->p2p)
+        for (int r = 0; r < h->nranks; ++r)
+            for (int b = 0; b < 2; ++b)
+                if (r != h->rank && h->peerY[b][r]) cudaIpcCloseMemHandle(h->peerY[b][r]);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -644,7 +685,7 @@ static int create_impl(niwqg_handle* h) {
     DA(h->qh[0], ssz); DA(h->ph, ssz); DA(h->uv, fsz); DA(h->qs, fsz);
     DA(h->P1, fsz); DA(h->P2, fsz); DA(h->W, fsz);
     DA(h->rscratch, B * h->npts * sizeof(double));
-    if (h->nranks > 1) { DA(h->X, fsz); DA(h->Y, fsz); }
+    if (h->nranks > 1) { DA(h->X, fsz); DA(h->Y, fsz); DA(h->Yp[0], fsz); DA(h->Yp[1], fsz); DA(h->bar, 64); }
     if (p.model != NIWQG_MODEL_YBJ) { DA(h->qh[1], ssz); DA(h->y1q, ssz); DA(h->F0q, ssz); DA(h->Fabq, ssz); }
     if (!h->qg) {
         DA(h->phih[0], ssz); DA(h->phih[1], ssz); DA(h->y1p, ssz); DA(h->F0p, ssz); DA(h->Fabp, ssz);
@@ -695,6 +736,34 @@ int niwqg_nccl_unique_id(char* out128) {
     ncclUniqueId id;
     if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return -5; }
     memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+int niwqg_ipc_export(niwqg_handle* h, char* out, size_t bytes) {
+    if (bytes < 2 * sizeof(cudaIpcMemHandle_t)) { h->err = "ipc_export: buffer too small"; return -1; }
+    if (h->nranks <= 1) { h->err = "ipc_export: not a slab handle"; return -1; }
+    CK(cudaSetDevice(h->p.device));
+    for (int b = 0; b < 2; ++b) {
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, h->Yp[b]));
+        memcpy(out + b * sizeof mh, &mh, sizeof mh);
+    }
+    return 0;
+}
+
+int niwqg_ipc_import(niwqg_handle* h, const char* all, size_t bytes_per_rank) {
+    if (h->nranks <= 1 || h->nranks > 8) { h->err = "ipc_import: 2..8 ranks"; return -1; }
+    CK(cudaSetDevice(h->p.device));
+    for (int r = 0; r < h->nranks; ++r)
+        for (int b = 0; b < 2; ++b) {
+            if (r == h->rank) { h->peerY[b][r] = h->Yp[b]; continue; }
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, all + (size_t)r * bytes_per_rank + b * sizeof mh, sizeof mh);
+            void* ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+            h->peerY[b][r] = (cd*)ptr;
+        }
+    h->p2p = true;
     return 0;
 }
 

@@ -48,7 +48,24 @@ def make_model(model_cls, dist=None, device=None, **kw):
         device = torch.cuda.current_device()
     if world == 1:
         return model_cls(device=device, **kw)
-    return model_cls(device=device, rank=rank, nranks=world, nccl_id=share_unique_id(dist), **kw)
+    m = model_cls(device=device, rank=rank, nranks=world, nccl_id=share_unique_id(dist), **kw)
+    import os
+    if os.environ.get("NIWQG_SLAB_NCCL", "0") != "1":
+        enable_peer_exchange(m, dist)
+    return m
+
+
+def enable_peer_exchange(model, dist):
+    """All-gather the CUDA-IPC handles of every rank's receive buffers and map them: the transposes of the distributed
+    FFT are then stores into peer memory over NVLink, fused into the FFT pass kernels (no ncclSend/ncclRecv)."""
+    import torch
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(model._h.ipc_export()), dtype=torch.uint8, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(model.nranks)]
+    dist.all_gather(parts, mine)
+    model._h.ipc_import(b"".join(bytes(p.cpu().tolist()) for p in parts))
+    dist.barrier()
 
 
 def gather_rows(model, local, dist=None):
