@@ -5,9 +5,12 @@
 
 Metric (BASELINE.json): fp64 grid-point-steps/s of the coupled NIW-QG model.
 Default workload: CoupledModel, Lamb dipole + uniform NIW, 8192^2, fp64, exponential filter on
-(the grid the north-star target is stated on; 34.5 GiB resident, so one member per GPU).  With
-N > 1 every rank steps its own independent member (ensemble sharding, no data-path collective):
-weak scaling.  One "step" = one _step_etdrk4 of every member.
+(the grid the north-star target is stated on; 34.5 GiB resident on one GPU).  With N > 1 the SAME
+8192^2 grid is slab-decomposed over the N GPUs (BASELINE config 4: rows of the physical fields / columns of
+the spectra per rank, the distributed-FFT transposes fused into the FFT passes as stores into peer memory
+over NVLink): strong scaling, "value" = grid-point-steps/s of the one big grid.  `--mode ensemble` instead
+steps one independent member per GPU (BASELINE config 5 style, no data-path collective): weak scaling; at
+N > 1 the default run reports it too under "ensemble_weak".  One "step" = one _step_etdrk4.
 
 Keys beyond the base contract: `roofline` (dominant kernel: the FFT pass, live CUDA-event timing),
 `step_roofline` (whole step against the algorithmic 3392 B/point model of SURVEY.md section 8d),
@@ -144,26 +147,36 @@ def run_ours(args):
         ge.build()
     if dist is not None:
         dist.barrier()
-    from niwqg_b200 import CoupledModel, _native as nat
+    from niwqg_b200 import CoupledModel, slab, _native as nat
 
     model_name, nx, batch = WORKLOADS[args.workload]
+    slab_mode = world > 1 and args.mode == "slab"
+    if slab_mode and batch != 1:
+        raise SystemExit("slab mode needs a single-member workload")
     kw, U0, k0 = workload_params(nx)
     kw_e2e = dict(kw)
     kw_e2e["tdiags"] = 1
-    m = CoupledModel.Model(batch=batch, device=local, **kw_e2e)
-    q, phi = initial_conditions(m, U0, k0, batch, seed0=rank)
+    if slab_mode:
+        m = slab.make_model(CoupledModel.Model, dist=dist, device=local, **kw_e2e)
+        q, phi = initial_conditions(m, U0, k0, batch, seed0=0)
+        lo, hi = slab.rows_of(rank, world, nx)
+        q, phi = np.ascontiguousarray(q[lo:hi]), np.ascontiguousarray(phi[lo:hi])
+    else:
+        m = CoupledModel.Model(batch=batch, device=local, **kw_e2e)
+        q, phi = initial_conditions(m, U0, k0, batch, seed0=rank)
+    nyl = nx // world if slab_mode else nx
     # pinned host buffers (torch is used for pinned/host plumbing and the process group only)
     q_pin = torch.empty(q.shape, dtype=torch.float64).pin_memory()
     phi_pin = torch.empty(phi.shape, dtype=torch.complex128).pin_memory()
     q_pin.numpy()[...] = q
     phi_pin.numpy()[...] = phi
-    qo_pin = torch.empty((nx, nx), dtype=torch.float64).pin_memory()
-    po_pin = torch.empty((nx, nx), dtype=torch.complex128).pin_memory()
+    qo_pin = torch.empty((nyl, nx), dtype=torch.float64).pin_memory()
+    po_pin = torch.empty((nyl, nx), dtype=torch.complex128).pin_memory()
     del q, phi
     m.set_q(q_pin.numpy())
     m.set_phi(phi_pin.numpy())
     h = m._h
-    npts = batch * nx * nx
+    npts = batch * nyl * nx          # grid points this rank steps
 
     def barrier():
         if dist is not None:
@@ -186,7 +199,7 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * npts * args.steps / (ms * 1e-3)
+    value = world * npts * args.steps / (ms * 1e-3)     # slab: world * (nx^2 / world) = the one grid
 
     # ---------------- per-kernel-kind timing (separate short run with events around every launch)
     nprof = min(args.steps, 3)
@@ -217,9 +230,28 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_val = world * npts * ne / e2e_s
     h2d = npts * 8 + npts * 16
-    d2h = nx * nx * 24 + nat.S_COUNT * 8 * batch
+    d2h = nyl * nx * 24 + nat.S_COUNT * 8 * batch
     diag_ke = m.diagnostics["ke_qg"]["value"]
 
+    ens = None
+    if slab_mode and not args.no_ensemble:
+        # the other natural partition of the north star: one independent member per GPU, no collective (weak scaling)
+        h.close()
+        del m, h
+        me = CoupledModel.Model(batch=1, device=local, **kw)
+        qe, pe = initial_conditions(me, U0, k0, 1, seed0=rank)
+        me.set_q(qe); me.set_phi(pe)
+        del qe, pe
+        me._h.step(args.warmup)
+        barrier_e = lambda: (dist.barrier(), torch.cuda.synchronize(), me._h.sync())
+        barrier_e()
+        ms_e = me._h.time_steps(args.steps)
+        barrier_e()
+        t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ens = {"value": world * nx * nx * args.steps / (float(t.item()) * 1e-3), "unit": UNIT, "scaling": "weak",
+               "ms_per_step": float(t.item()) / args.steps,
+               "what": "one independent %d^2 member per GPU, no data-path collective" % nx}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -240,13 +272,18 @@ def run_ours(args):
         pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if slab_mode else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "CoupledModel Lamb dipole + uniform NIW %d^2 fp64, exponential filter, %d member(s)/GPU (%s)"
                                % (nx, batch, args.workload),
-                   "parallelism": "ensemble: one member batch per GPU, no data-path collective" if world > 1 else "single GPU",
+                   "parallelism": ("slab decomposition of the one grid over %d GPUs: rows/columns per rank, FFT transposes "
+                                   "fused into the FFT passes as peer-memory stores over NVLink (%s), all-reduced budget sums"
+                                   % (world, "CUDA IPC" if os.environ.get("NIWQG_SLAB_NCCL", "0") != "1" else "NCCL all-to-all"))
+                                  if slab_mode else
+                                  ("ensemble: one member batch per GPU, no data-path collective" if world > 1 else "single GPU"),
                    "l2": "working set %.1f GiB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
-                         % (batch * nx * nx * 16 * 34.5 / 2 ** 30) if nx * nx * batch * 16 * 30 > 4e8 else
+                         % (batch * nyl * nx * 16 * 34.5 / 2 ** 30) if nx * nyl * batch * 16 * 30 > 4e8 else
                          "working set fits in L2: not an HBM-bound measurement"},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -265,6 +302,8 @@ def run_ours(args):
         "kernel_breakdown": {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof} for k, v in prof.items()},
         "sanity": {"ke_qg_last": float(np.ravel(diag_ke)[-1]), "finite": bool(np.all(np.isfinite(diag_ke)))},
     }
+    if ens is not None:
+        out["ensemble_weak"] = ens
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(budget_s=25.0)
     print(json.dumps(out), flush=True)
@@ -369,6 +408,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="coupled8192", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="slab", choices=["slab", "ensemble"],
+                    help="N > 1: slab-decompose the one grid (strong scaling, default) or one member per GPU (weak)")
+    ap.add_argument("--no-ensemble", action="store_true", help="N > 1 slab run: skip the extra ensemble_weak measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
