@@ -18,6 +18,8 @@ enum {
     MF_NO_WRITE  = 1 << 5,   // diagnostics tick: sums only
     MF_SKIP_P1   = 1 << 6,   // [D] second half of a QL stage: P2 only, no sums
     MF_SKIP_P2   = 1 << 7,   // [D] first half of a QL stage: P1 + sums only
+    MF_SPEC_BUDGET = 1 << 8, // Coupled / UnCoupled: the stage budgets' lapphi terms are evaluated in spectral space
+                             // (Parseval, see k_spec_stage), so lapphi / lap2phi are not transformed during a step
 };
 
 // Grid (N, dk, local spectral columns, slab ownership) and the column maps grid_kx / grid_partner: common.cuh
@@ -153,7 +155,12 @@ struct InvertArgs {
     const cd* qh;
     const double* filtr;
     cd *qwh, *ph, *qs, *uvgen;   // uvgen: general packed (u + i v) spectrum (YBJ: from ph; QL: from ph_q)
+    double* partials;            // [member][block][SI_COUNT] Parseval sums of ep_psi (Kernel.py:635-640); may be null
 };
+
+// sums over the full spectrum on the state the NEXT stage starts from:
+//   [0] sum wv2^2 Re(qh conj ph)   [1] sum -wv2 Re(qh conj ph)   [2] sum Re(qh conj ph)      (ph Hermitian)
+enum { SI_QLAP2PSI = 0, SI_PLAPQ, SI_PQ, SI_COUNT };
 
 __device__ __forceinline__ void pack_uv_general(double k1, double l1, double k2, double l2, cd G1, cd G2,
                                                 cd& out1, cd& out2) {
@@ -167,7 +174,8 @@ __device__ __forceinline__ void pack_uv_general(double k1, double l1, double k2,
     out2 = make_double2(HU.x + HV.y, -HU.y + HV.x);
 }
 
-__global__ void k_spec_invert(InvertArgs a) {
+__global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_invert(InvertArgs a) {
+    double s[SI_COUNT] = {0.0, 0.0, 0.0};
     const int N = a.g.N, H = N >> 1, NC = a.g.ncl;
     const size_t npts = (size_t)N * NC, mb = (size_t)blockIdx.y * npts;
     const size_t total = (size_t)(H + 1) * NC;
@@ -205,6 +213,12 @@ __global__ void k_spec_invert(InvertArgs a) {
             qw.y = 0.5 * (0.5 * (-wv2 * A.y) + Jc.y) / a.f * fl;
         }
         const cd ph1 = make_double2(wv2i * qw.x - wv2i * Hq.x, wv2i * qw.y - wv2i * Hq.y);
+        {   // Re(Hq conj ph(K)) + Re(conj(Hq) conj ph(-K)), ph(-K) = conj ph(K)
+            const double r = (self ? 1.0 : 2.0) * (Hq.x * ph1.x + Hq.y * ph1.y);
+            s[SI_QLAP2PSI] += wv2 * wv2 * r;
+            s[SI_PLAPQ] += -wv2 * r;
+            s[SI_PQ] += r;
+        }
         // qs(K) = Hq + i qw ; qs(-K) = conj(Hq) + i conj(qw)
         a.ph[i1] = ph1;
         a.qs[i1] = make_double2(Hq.x - qw.y, Hq.y + qw.x);
@@ -215,6 +229,7 @@ __global__ void k_spec_invert(InvertArgs a) {
             if (a.qwh) a.qwh[i2] = make_double2(qw.x, -qw.y);
         }
     }
+    if (a.partials) block_reduce_store<SI_COUNT>(s, a.partials);
 }
 
 // QL wave advection velocity (QLModel.py:65-66): packed spectrum of Re ifft(-il ph_q) + i Re ifft(ik ph_q),
@@ -297,6 +312,15 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_phys_rhs(PhysArgs a) {
                 a.P2[mb + i] = make_double2(-Jadv.x + 0.5 * phi.y * qpsi, -Jadv.y - 0.5 * phi.x * qpsi);
         }
         if (nosums) continue;
+        s[SD_PHI_R] += phi.x; s[SD_PHI_I] += phi.y;
+        s[SD_QPC_R] += qpsi * phi.x; s[SD_QPC_I] += -qpsi * phi.y;
+        s[SD_PHI2] += phi.x * phi.x + phi.y * phi.y;
+        s[SD_GRAD2] += px.x * px.x + px.y * px.y + py.x * py.x + py.y * py.y;
+        s[SD_J_R] += Jadv.x; s[SD_J_I] += Jadv.y;
+        s[SD_Q2] += q * q;
+        s[SD_QP2] += qpsi * qpsi;
+        s[SD_QP3] += qpsi * qpsi * qpsi;
+        if (a.flags & MF_SPEC_BUDGET) continue;      // the lapphi terms come from k_spec_stage
         const cd lp = a.lapphi[mb + i];
         cd diss = make_double2(a.nuw * lp.x - a.muw * phi.x, a.nuw * lp.y - a.muw * phi.y);
         if (a.flags & MF_HAS_LAP2) {
@@ -307,15 +331,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_phys_rhs(PhysArgs a) {
         s[SD_G2] += lp.x * J.x + lp.y * J.y;                          // Re(conj(lap) J)
         s[SD_X1] += -(diss.y * J.x - diss.x * J.y);                   // -Im(diss conj(J))
         s[SD_X2] += 0.5 * (diss.x * phi.x + diss.y * phi.y) * qpsi;   // 0.5 Re(diss conj(phi)) q_psi
-        s[SD_PHI_R] += phi.x; s[SD_PHI_I] += phi.y;
-        s[SD_QPC_R] += qpsi * phi.x; s[SD_QPC_I] += -qpsi * phi.y;
-        s[SD_PHI2] += phi.x * phi.x + phi.y * phi.y;
-        s[SD_GRAD2] += px.x * px.x + px.y * px.y + py.x * py.x + py.y * py.y;
         s[SD_LAP2] += lp.x * lp.x + lp.y * lp.y;
-        s[SD_J_R] += Jadv.x; s[SD_J_I] += Jadv.y;
-        s[SD_Q2] += q * q;
-        s[SD_QP2] += qpsi * qpsi;
-        s[SD_QP3] += qpsi * qpsi * qpsi;
     }
     if (!nosums) block_reduce_store<SD_COUNT>(s, a.partials);
 }
@@ -335,7 +351,12 @@ __global__ void k_finalize(const double* __restrict__ partials, int nblk, int K,
 //     YBJModel.py:62-84) + the spectral budget sums (Parseval form of Kernel.py:635-640
 //     ep_psi and the nu4w term of :646-652 chi_phi), evaluated on the pre-update state.
 // ======================================================================
-enum { SE_QLAP2PSI = 0, SE_PLAPQ, SE_PQ, SE_WV6PHI, SE_COUNT };
+// Spectral budget sums of a stage (MF_SPEC_BUDGET), on the phih the stage starts from and the raw transform P2h of
+// P2 = -J(psi,phi) - 0.5i phi q_psi.  With lap = ifft(-wv2 phih), diss = ifft((-nu4w wv4 - nuw wv2 - muw) phih):
+//   mean Re(conj(lap) P2)  = -(0.5 G1 + G2)   so  gamma1 + gamma2 = 0.5 hslash Re(T1) / (M^2 f)
+//   mean Im(diss conj(P2)) =  X1 + X2         so  xi1 + xi2 = (-nu4w Im T2 - nuw Im T1 - muw Im T0) / (M^2 f)
+// where Tn = sum_K wv2^n phih(K) conj(P2h(K))  (Parseval; G1, G2, X1, X2 as in k_phys_rhs, Kernel.py:684-700).
+enum { SE_T0R = 0, SE_T0I, SE_T1R, SE_T1I, SE_T2R, SE_T2I, SE_LAP2, SE_WV6PHI, SE_COUNT };
 
 struct StageArgs {
     Grid g;
@@ -389,12 +410,22 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
         const size_t i1 = mb + t1, i2 = mb + t2;
         const bool self = (t1 == t2);
         const double fl1 = a.filtr[t1], fl2 = a.filtr[t2];
-        if (a.do_q && (a.flags & MF_HAS_LAP2)) {   // nu4w term of chi_phi on the pre-update phih (Kernel.py:648-650)
+        const bool specb = (a.flags & MF_SPEC_BUDGET) != 0;
+        if (a.do_q && (specb || (a.flags & MF_HAS_LAP2))) {   // |phih|^2 moments on the pre-update phih (Kernel.py:629-652)
             const cd c1 = (st == 1) ? a.y0p[i1] : a.yp[i1], c2 = (st == 1) ? a.y0p[i2] : a.yp[i2];
             const double k1 = a.g.dk * (double)sidx(kx, N), l1 = a.g.dk * (double)sidx(ky, N);
-            const double wv2 = k1 * k1 + l1 * l1, w6 = wv2 * wv2 * wv2;
-            s[SE_WV6PHI] += w6 * (c1.x * c1.x + c1.y * c1.y);
-            if (!self) s[SE_WV6PHI] += w6 * (c2.x * c2.x + c2.y * c2.y);
+            const double wv2 = k1 * k1 + l1 * l1, w4 = wv2 * wv2;
+            const double m2 = (c1.x * c1.x + c1.y * c1.y) + (self ? 0.0 : (c2.x * c2.x + c2.y * c2.y));
+            s[SE_LAP2] += w4 * m2;
+            s[SE_WV6PHI] += w4 * wv2 * m2;
+            if (specb) {
+                const cd F1 = a.P2[i1], F2 = a.P2[i2];   // raw transform, before the (0,0) fix
+                double zr = c1.x * F1.x + c1.y * F1.y, zi = c1.y * F1.x - c1.x * F1.y;
+                if (!self) { zr += c2.x * F2.x + c2.y * F2.y; zi += c2.y * F2.x - c2.x * F2.y; }
+                s[SE_T0R] += zr; s[SE_T0I] += zi;
+                s[SE_T1R] += wv2 * zr; s[SE_T1I] += wv2 * zi;
+                s[SE_T2R] += w4 * zr; s[SE_T2I] += w4 * zi;
+            }
         }
         // ---------------- phi equation
         if (a.do_phi) {
@@ -435,24 +466,11 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
             cd F1 = make_double2(k1 * A.y + l1 * B.y, -(k1 * A.x + l1 * B.x));
             cd F2 = make_double2(-(k2 * A.y + l2 * B.y), -(k2 * A.x + l2 * B.x));
             if (mode00) { F1 = make_double2(0.0, 0.0); F2 = F1; }
-            const cd cur1 = (st == 1) ? a.y0q[i1] : a.yq[i1];
-            const cd cur2 = (st == 1) ? a.y0q[i2] : a.yq[i2];
-            {   // budget sums on the pre-update state
-                const double wv2 = k1 * k1 + l1 * l1;
-                const cd Hq = make_double2(0.5 * (cur1.x + cur2.x), 0.5 * (cur1.y - cur2.y));
-                const cd ph1 = a.ph[i1], ph2 = a.ph[i2];
-                // Re(Hq conj(ph(K))) + Re(conj(Hq) conj(ph(-K)))
-                double r = Hq.x * ph1.x + Hq.y * ph1.y;
-                if (!self) r += Hq.x * ph2.x - Hq.y * ph2.y;
-                s[SE_QLAP2PSI] += wv2 * wv2 * r;
-                s[SE_PLAPQ] += -wv2 * r;
-                s[SE_PQ] += r;
-            }
             cd F0a, F0b, Faba, Fabb, y1a, y1b;
             if (st >= 3) { F0a = a.F0q[i1]; F0b = a.F0q[i2]; }
             if (st >= 3) { Faba = a.Fabq[i1]; Fabb = a.Fabq[i2]; }
             if (st == 3) { y1a = a.y1q[i1]; y1b = a.y1q[i2]; }
-            const cd b1 = (st == 1) ? cur1 : a.y0q[i1], b2 = (st == 1) ? cur2 : a.y0q[i2];
+            const cd b1 = a.y0q[i1], b2 = a.y0q[i2];      // the ep_psi sums of this state: k_spec_invert
             const cd n1 = etd_update(st, b1, y1a, F1, F0a, Faba, a.tq, t1, fl1);
             a.yq[i1] = n1;
             if (st == 1) { a.F0q[i1] = F0a; a.y1q[i1] = n1; }
@@ -477,7 +495,8 @@ struct BudgetArgs {
     double M;            // N*N
     double f, hslash, kappa2, dt;
     double nu4, nu, mu, nu4w, nuw, muw;
-    const double *sumsD, *sumsE;
+    const double *sumsD, *sumsE, *sumsI;   // physical (k_phys_rhs), stage-spectral (k_spec_stage), k_spec_invert
+    int spec_budget;
     double* scal;        // [member][NIWQG_S_COUNT]
     double* stagev;      // [member][4][3]
 };

@@ -61,7 +61,8 @@ struct niwqg_handle {
     cd *W = nullptr, *P1 = nullptr, *P2 = nullptr;
     double* rscratch = nullptr;   // [B][N][N] doubles
     // reductions
-    double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *scal = nullptr, *stagev = nullptr;
+    double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *sumsI = nullptr, *scal = nullptr,
+           *stagev = nullptr;
     bool q_set = false, phi_set = false;
     // slab decomposition over nranks GPUs (one process per GPU): physical arrays hold nyl = N/P rows, spectral
     // arrays all N rows of ncl = N/P columns (Grid, common.cuh); each 2-D transform = local pass, NCCL all-to-all,
@@ -304,18 +305,29 @@ __global__ void k_budget(BudgetArgs a) {
     if (threadIdx.x != 0) return;
     const double* sd = a.sumsD + (size_t)m * SD_COUNT;
     const double* se = a.sumsE + (size_t)m * SE_COUNT;
+    const double* si = a.sumsI + (size_t)m * SI_COUNT;
     double* sc = a.scal + (size_t)m * NIWQG_S_COUNT;
-    const double M = a.M;
-    const double g1 = 0.5 * 0.5 * a.hslash * (sd[SD_G1] / M) / a.f;
-    const double g2 = 0.5 * a.hslash * (sd[SD_G2] / M) / a.f;
-    const double x1 = (sd[SD_X1] / M) / a.f, x2 = (sd[SD_X2] / M) / a.f;
+    const double M = a.M, M2 = M * M;
+    double g1, g2, x1, x2, lap2m;
+    if (a.spec_budget) {
+        // only the sums gamma1+gamma2 and xi1+xi2 enter the stage tendencies (Kernel.py:320-321); Parseval forms
+        g1 = 0.5 * a.hslash * (se[SE_T1R] / M2) / a.f;
+        g2 = 0.0;
+        x1 = ((-a.nu4w * se[SE_T2I] - a.nuw * se[SE_T1I] - a.muw * se[SE_T0I]) / M2) / a.f;
+        x2 = 0.0;
+        lap2m = se[SE_LAP2] / M2;
+    } else {
+        g1 = 0.5 * 0.5 * a.hslash * (sd[SD_G1] / M) / a.f;
+        g2 = 0.5 * a.hslash * (sd[SD_G2] / M) / a.f;
+        x1 = (sd[SD_X1] / M) / a.f; x2 = (sd[SD_X2] / M) / a.f;
+        lap2m = sd[SD_LAP2] / M;
+    }
     const double ar = sd[SD_PHI_R] / M, ai = sd[SD_PHI_I] / M, br = sd[SD_QPC_R] / M, bi = sd[SD_QPC_I] / M;
     const double pi = 0.5 * (ar * bi + ai * br);
-    const double M2 = M * M;
-    const double ep_psi = a.nu4 * (se[SE_QLAP2PSI] / M2) - a.nu * (se[SE_PLAPQ] / M2) + a.mu * (se[SE_PQ] / M2);
-    const double chi_phi = -0.5 * a.nu4w * (se[SE_WV6PHI] / M2) / a.kappa2 - 0.5 * a.nuw * (sd[SD_LAP2] / M) / a.kappa2 -
+    const double ep_psi = a.nu4 * (si[SI_QLAP2PSI] / M2) - a.nu * (si[SI_PLAPQ] / M2) + a.mu * (si[SI_PQ] / M2);
+    const double chi_phi = -0.5 * a.nu4w * (se[SE_WV6PHI] / M2) / a.kappa2 - 0.5 * a.nuw * lap2m / a.kappa2 -
                            0.5 * a.muw * (sd[SD_GRAD2] / M) / a.kappa2;
-    const double ep_phi = -a.nu4w * (sd[SD_LAP2] / M) - a.nuw * (sd[SD_GRAD2] / M) - a.muw * (sd[SD_PHI2] / M);
+    const double ep_phi = -a.nu4w * lap2m - a.nuw * (sd[SD_GRAD2] / M) - a.muw * (sd[SD_PHI2] / M);
     sc[NIWQG_S_GAMMA1] = g1; sc[NIWQG_S_GAMMA2] = g2; sc[NIWQG_S_XI1] = x1; sc[NIWQG_S_XI2] = x2; sc[NIWQG_S_PI] = pi;
     if (a.stage == 0) {
         sc[NIWQG_S_EP_PSI] = ep_psi; sc[NIWQG_S_CHI_PHI] = chi_phi; sc[NIWQG_S_EP_PHI] = ep_phi;
@@ -337,7 +349,8 @@ static BudgetArgs budget_args(niwqg_handle* h, int stage) {
     BudgetArgs b{};
     b.stage = stage; b.M = h->Mg; b.f = h->p.f; b.hslash = h->hslash; b.kappa2 = h->kappa2; b.dt = h->p.dt;
     b.nu4 = h->p.nu4; b.nu = h->p.nu; b.mu = h->p.mu; b.nu4w = h->p.nu4w; b.nuw = h->p.nuw; b.muw = h->p.muw;
-    b.sumsD = h->sumsD; b.sumsE = h->sumsE; b.scal = h->scal; b.stagev = h->stagev;
+    b.sumsD = h->sumsD; b.sumsE = h->sumsE; b.sumsI = h->sumsI; b.scal = h->scal; b.stagev = h->stagev;
+    b.spec_budget = (h->flags & MF_SPEC_BUDGET) ? 1 : 0;
     return b;
 }
 
@@ -373,9 +386,11 @@ static int invert_family(niwqg_handle* h) {
         ia.W = h->W; ia.qwh = h->qwh; ia.inv_jscale = 1.0 / h->jscale;
     }
     if (h->flags & MF_YBJ) ia.uvgen = h->uv;
+    ia.partials = (h->flags & MF_YBJ) ? nullptr : h->part;
     { PROF(PK_SPEC); k_spec_invert<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(ia); }
     CK(cudaGetLastError());
     h->launches++;
+    if (ia.partials) FIN(SI_COUNT, h->sumsI);   // ep_psi sums of the state the next stage starts from
     if (h->flags & MF_YBJ) {
         FFT(h->uv, h->uv, true, PRO_NONE, h->B);
     } else {
@@ -465,7 +480,7 @@ static int step_family(niwqg_handle* h) {
             h->launches++;
             // self.phi = ifft(phih); _invert(); _calc_rel_vorticity()  (Kernel.py:337-339 / :395-397)
             const bool grad = (h->flags & MF_WAVE_PV) != 0;   // only jacobian_phic_phi refreshes phix, phiy (F6)
-            int r = wave_fields(h, true, grad, true);
+            int r = wave_fields(h, true, grad, !(h->flags & MF_SPEC_BUDGET));
             if (r) return r;
             r = invert_family(h);
             if (r) return r;
@@ -621,13 +636,14 @@ static int create_impl(niwqg_handle* h) {
         h->hslash = p.f / h->kappa2;
     }
     switch (p.model) {
-        case NIWQG_MODEL_COUPLED: h->flags = MF_WAVE_PV | MF_FIX00; break;
-        case NIWQG_MODEL_UNCOUPLED: h->flags = MF_FIX00; break;
+        case NIWQG_MODEL_COUPLED: h->flags = MF_WAVE_PV | MF_FIX00 | MF_SPEC_BUDGET; break;
+        case NIWQG_MODEL_UNCOUPLED: h->flags = MF_FIX00 | MF_SPEC_BUDGET; break;
         case NIWQG_MODEL_YBJ: h->flags = MF_YBJ; break;
         case NIWQG_MODEL_QL: h->flags = MF_WAVE_PV | MF_QL_ADV; break;
         default: h->flags = 0;
     }
     if (!h->qg && p.nu4w != 0.0) h->flags |= MF_HAS_LAP2;
+    if (getenv("NIWQG_NO_SPEC_BUDGET")) h->flags &= ~MF_SPEC_BUDGET;   // A/B knob: physical-space budget sums
     const size_t B = h->B, cb = sizeof(cd);
     const size_t fsz = B * h->npts * cb, ssz = B * h->nspec * cb, tsz = h->nspec * cb;
     // twiddles
@@ -698,6 +714,7 @@ static int create_impl(niwqg_handle* h) {
     }
     DA(h->part, B * NIWQG_PW_BLOCKS * 16 * sizeof(double));
     DA(h->sumsD, B * 16 * sizeof(double)); DA(h->sumsE, B * 16 * sizeof(double)); DA(h->sumsX, B * 16 * sizeof(double));
+    DA(h->sumsI, B * 16 * sizeof(double));
     DA(h->scal, B * NIWQG_S_COUNT * sizeof(double)); DA(h->stagev, B * 24 * sizeof(double));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -882,8 +899,10 @@ int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
     CK(cudaGetLastError());
     h->launches += 3;
     // lapphi follows phih (the reference recomputes it at every _calc_energy_conversion, Kernel.py:685)
-    r = wave_fields(h, false, false, true);
-    if (r) return r;
+    if (!(h->flags & MF_SPEC_BUDGET)) {
+        r = wave_fields(h, false, false, true);
+        if (r) return r;
+    }
     h->phi_set = true;
     return 0;
 }
@@ -1070,12 +1089,14 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
     }
     // ---- kernel family: _calc_energy_conversion on the current state (stale phix/phiy for UnCoupled, F6)
     const bool ybj = (h->flags & MF_YBJ) != 0;
-    if (ybj) {   // lapphi = ifft(-wv2*phih) is recomputed by every _calc_energy_conversion (Kernel.py:685)
+    if (ybj || (h->flags & MF_SPEC_BUDGET)) {
+        // lapphi = ifft(-wv2*phih) is recomputed by every _calc_energy_conversion (Kernel.py:685); during a step the
+        // spectral-budget models never transform it, so the tick does
         int r0 = wave_fields(h, false, false, true);
         if (r0) return r0;
     }
     PhysArgs pa = phys_args(h, MF_NO_WRITE);
-    pa.flags &= ~MF_YBJ;   // the tick evaluates the full budget terms for every family model
+    pa.flags &= ~(MF_YBJ | MF_SPEC_BUDGET);   // the tick evaluates every budget term separately, in physical space
     { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
     CK(cudaGetLastError());
     FIN(SD_COUNT, h->sumsD);
@@ -1196,7 +1217,13 @@ int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t by
         case NIWQG_F_PHIH: src = h->phih[h->cp] ? h->phih[h->cp] + so : nullptr; break;
         case NIWQG_F_PHIX: src = h->phix ? h->phix + mo : nullptr; break;
         case NIWQG_F_PHIY: src = h->phiy ? h->phiy + mo : nullptr; break;
-        case NIWQG_F_LAPPHI: src = h->lapphi ? h->lapphi + mo : nullptr; break;
+        case NIWQG_F_LAPPHI:
+            if (h->lapphi && (h->flags & MF_SPEC_BUDGET)) {   // not carried during steps: evaluate from the current phih
+                int r0 = wave_fields(h, false, false, true);
+                if (r0) return r0;
+            }
+            src = h->lapphi ? h->lapphi + mo : nullptr;
+            break;
         case NIWQG_F_QWH: src = h->qwh ? h->qwh + so : nullptr; break;
         case NIWQG_F_CH: src = h->chh[h->cc] ? h->chh[h->cc] + so : nullptr; break;
         case NIWQG_F_FILTR: src = h->filtr; break;
