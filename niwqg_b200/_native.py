@@ -11,6 +11,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libniwqg_b200.so")
+if os.environ.get("NIWQG_LIB"):          # development: an alternative build of the same library
+    LIB_PATH = os.environ["NIWQG_LIB"]
 
 MODEL_QG, MODEL_COUPLED, MODEL_UNCOUPLED, MODEL_YBJ, MODEL_QL = range(5)
 

@@ -68,7 +68,8 @@ struct FftArgs {
     int nyl_shift;    // log2(rows per rank)
     cd* peer[8];      // receive buffer of every rank (peer[rank] = own), CUDA-IPC mapped
     size_t mstride;   // elements between ensemble members
-    int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel
+    int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel;
+                      // bit 2 = the push kernel uses plain remote stores + a cluster barrier instead of st.async
 };
 
 // element n of line `line`: offset inside one member's array
@@ -136,7 +137,7 @@ template <int M, int W, int C, bool COL> struct Tile {
     static constexpr int T = W * TPF;            // threads per CTA
     static constexpr int LINE = fftc::phys_len(M);
     static constexpr int TWLEN = fftc::tw_table_len(M) + 1;           // stage twiddles, copied to shared memory
-    static constexpr size_t SMEM = ((size_t)W * LINE + TWLEN) * sizeof(cd);
+    static constexpr size_t SMEM = ((size_t)W * LINE + TWLEN + 1) * sizeof(cd);   // + one slot for an mbarrier
     static constexpr int MINB = (T <= 256) ? 2 : 1;   // resident CTAs per SM the register budget is cut for
     __device__ static __forceinline__ int slot(int w, int o) {
         return COL ? fftc::phys(o) * W + w : w * LINE + fftc::phys(o);
@@ -191,6 +192,36 @@ __device__ __forceinline__ void cluster_arrive_relaxed_after(double dep) {
     asm volatile("{\n\t.reg .f64 t;\n\tmov.f64 t, %0;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\t}" ::"d"(dep) : "memory");
 }
 __device__ __forceinline__ void cluster_wait_relaxed() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+
+// ---- asynchronous distributed-shared-memory stores (st.async): the store lands in a peer CTA's shared memory and
+// credits its byte count to the peer's mbarrier, so the producer needs no fence and the consumer waits only for its
+// own incoming bytes
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_map_u32(unsigned local_addr, int rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_async_cd(unsigned remote_addr, cd x, unsigned remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                 ::"r"(remote_addr), "d"(x.x), "d"(x.y), "r"(remote_bar) : "memory");
+}
 
 // L2 prefetch of the tile that the CTA `pf_groups` line groups ahead will load: the DRAM latency of that tile
 // is paid while the tiles in between are transformed, so a CTA's own loads are (mostly) L2 hits.
@@ -331,7 +362,9 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 //   STORES it into CTA q's shared memory (st.shared::cluster: fire and forget, nobody waits for a remote load).
 //   After ONE cluster barrier CTA q holds its whole sub-sequence Y_q[0..M) and transforms it locally:
 //   X[C k + q] = FFT_M(Y_q)[k].  No CTA touches a peer's memory after the barrier, so no exit barrier is needed.
-template <int M, int W, int C, bool COL>
+// ASYNC: the pushes are st.async stores crediting the receiver's mbarrier (no producer fence, no cluster rendezvous
+// after the pushes; one cluster barrier at kernel start makes every mbarrier visible before anybody pushes).
+template <int M, int W, int C, bool COL, bool ASYNC>
 __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pass_dif(FftArgs a) {
     using TL = Tile<M, W, C, COL>;
     constexpr int N = TL::N;
@@ -347,6 +380,15 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     const int line = group * W + w;
     const size_t mbase = (size_t)blockIdx.y * a.mstride;
     cd* smtw = smem + (size_t)W * TL::LINE;
+    const unsigned bar = smem_u32(smtw + TL::TWLEN);
+    if constexpr (ASYNC) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            // every peer sends its (M/C) x W block of my sub-sequence; my own block is written with plain stores
+            mbar_expect_tx(bar, (unsigned)((C - 1) * (M / C) * W * sizeof(cd)));
+        }
+        cluster_arrive_release();          // ... and the loads below are in flight while the peers get here
+    }
     for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
     constexpr int PPT = fftc::E / C;                        // radix-C butterflies per thread
@@ -414,6 +456,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) v[e].y = -v[e].y;
     }
+    if constexpr (ASYNC) cluster_wait_acquire();            // all mbarriers of the cluster are initialised
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
         NIWQG_BF(i)
@@ -427,13 +470,24 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
         for (int p = 0; p < C; ++p) {
             const int q = fftc::outidx<C>(p);
-            cd* dst = cluster.map_shared_rank(smem, q);
-            dst[TL::slot(wq, m)] = (q == 0) ? v[i * C + p] : cmul(v[i * C + p], pw[q]);
+            const cd val = (q == 0) ? v[i * C + p] : cmul(v[i * C + p], pw[q]);
+            if constexpr (ASYNC) {
+                if (q == c) smem[TL::slot(wq, m)] = val;
+                else st_async_cd(cluster_map_u32(smem_u32(smem + TL::slot(wq, m)), q), val, cluster_map_u32(bar, q));
+            } else {
+                cd* dst = cluster.map_shared_rank(smem, q);
+                dst[TL::slot(wq, m)] = val;
+            }
         }
     }
 #undef NIWQG_BF
-    cluster_arrive_release();
-    cluster_wait_acquire();
+    if constexpr (ASYNC) {
+        mbar_wait(bar, 0);       // the other C-1 blocks of my sub-sequence have landed
+        __syncthreads();         // my own block
+    } else {
+        cluster_arrive_release();
+        cluster_wait_acquire();
+    }
 #pragma unroll
     for (int e = 0; e < fftc::E; ++e) v[e] = smem[TL::slot(w, j + e * TL::TPF)];
     __syncthreads();
@@ -441,12 +495,21 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 }
 
 // ---- pass geometry: (M, W, C) per grid size
+#ifndef NIWQG_COL_M
+#define NIWQG_COL_M 1024      // local transform length of a column pass
+#endif
+#ifndef NIWQG_ROW_MAXM
+#define NIWQG_ROW_MAXM 4096   // longest line one CTA transforms alone in a row pass (longer lines: cluster)
+#endif
+#ifndef NIWQG_COL_TILE
+#define NIWQG_COL_TILE 4096   // points per CTA of a column pass
+#endif
 template <int N, bool COL> struct PassCfg {
     // column pass: W = 4 adjacent columns (64 B per row access), 1024-point local transforms for N >= 1024
     // row pass: whole line per CTA up to 4096 points, two CTAs per line at 8192
-    static constexpr int M = COL ? (N >= 1024 ? 1024 : N) : (N > 4096 ? 4096 : N);
+    static constexpr int M = COL ? (N >= NIWQG_COL_M ? NIWQG_COL_M : N) : (N > NIWQG_ROW_MAXM ? NIWQG_ROW_MAXM : N);
     static constexpr int C = N / M;
-    static constexpr int W = (M >= 512) ? 4096 / M : 8;
+    static constexpr int W = (COL && N >= NIWQG_COL_M) ? NIWQG_COL_TILE / M : ((M >= 4096) ? 1 : (M >= 512) ? 4096 / M : 8);
 };
 
 template <int N, bool COL>
@@ -459,7 +522,9 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
                                              (int)TL::SMEM);
         if (e != cudaSuccess) return e;
         if constexpr (C > 1) {
-            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
             if (e != cudaSuccess) return e;
         }
         attr_set = true;
@@ -480,13 +545,16 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     if (a.nlines % W) return cudaErrorInvalidValue;
     b.pf_groups = (a.pf_groups > 0 && (a.nlines / W) * C > 2 * a.pf_groups) ? (a.pf_groups + C - 1) / C : 0;   // CTAs -> groups
     if constexpr (C > 1) {
-        if (!(a.variant & (COL ? 1 : 2))) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL>, b);
+        if (!(a.variant & (COL ? 1 : 2))) {
+            if (a.variant & 4) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, false>, b);
+            return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, true>, b);
+        }
     }
     return cudaLaunchKernelEx(&cfg, k_fft_pass<M, W, C, COL>, b);
 }
 
 // local transform length of a pass (the stage twiddle table to bind)
-static inline int pass_local_len(int N, bool col) { return col ? (N >= 1024 ? 1024 : N) : (N > 4096 ? 4096 : N); }
+static inline int pass_local_len(int N, bool col) { return col ? (N >= NIWQG_COL_M ? NIWQG_COL_M : N) : (N > NIWQG_ROW_MAXM ? NIWQG_ROW_MAXM : N); }
 
 template <bool COL>
 static cudaError_t launch_pass(int N, const FftArgs& a, int batch, cudaStream_t st) {

@@ -78,7 +78,8 @@ struct niwqg_handle {
     int ybuf = 0;
     double* bar = nullptr;      // 1-element all-reduce buffer: the cross-GPU barrier between the two passes
     ncclComm_t comm = nullptr;
-    int fft_variant = 2;        // FftArgs::variant: column clusters push (DIF), row clusters pull (DIT) - measured best
+    int fft_variant = 6;        // FftArgs::variant: column clusters push (DIF, plain remote stores), row clusters pull (DIT):
+                                // measured best (profiles/r01b_cluster_variants.txt, r01d_async_push.txt)
     int pf_ctas = 296;          // L2 prefetch distance of the FFT passes in CTAs (~ one resident wave: 148 SMs x 2)
     // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg)
     bool prof = false;
