@@ -64,6 +64,8 @@ struct FftArgs {
     int pitch;        // column pass: elements between consecutive rows (N, or ncl in the slab layout)
     int xmap_in, xmap_out;   // row pass of a slab transform: load / store through the all-to-all exchange layout
     int xchunk;       // exchange layout: elements per peer chunk (nyl * ncl)
+    int deint_in, deint_out;   // row pass split over a cluster: the PHYSICAL side of the line is stored de-interleaved
+                      // (position c*M + m holds x = C*m + c), so both cluster kernels touch contiguous memory
     int push;         // slab: the pass's stores go straight into the owners' receive buffers over NVLink (peer[])
     int nyl_shift;    // log2(rows per rank)
     cd* peer[8];      // receive buffer of every rank (peer[rank] = own), CUDA-IPC mapped
@@ -151,7 +153,9 @@ __device__ __forceinline__ void fft_emit(const FftArgs& a, size_t mbase, int lin
     if constexpr (C == 1) {
         fft_store<TL::N, COL>(a, mbase, line, k, x);
     } else if constexpr (DIF) {
-        const int n = C * k + c;    // decimation in frequency: CTA c produced the outputs congruent to c mod C
+        const int n = a.deint_out ? c * M + k : C * k + c;    // decimation in frequency: CTA c produced the outputs
+                                                               // congruent to c mod C (stored as one contiguous block
+                                                               // when the physical side is de-interleaved)
         fft_store<TL::N, COL>(a, mbase, line, n, x);
     } else {
         smem[TL::slot(w, k)] = x;   // E_c[k]; the cluster twiddle w_N^{c k} is applied by the gathering CTA
@@ -272,14 +276,16 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
         const double* in = (const double*)a.in + mbase;
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) {
-            const int n = C * (j + e * TL::TPF) + c;       // decimated sub-sequence of CTA c
+            const int m_ = j + e * TL::TPF;
+            const int n = (C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
             v[e] = make_double2(in[fft_index<N, COL>(a, a.xmap_in, line, n)], 0.0);
         }
     } else {
         const cd* in = (const cd*)a.in + mbase;
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) {
-            const int n = C * (j + e * TL::TPF) + c;
+            const int m_ = j + e * TL::TPF;
+            const int n = (C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
             v[e] = in[fft_index<N, COL>(a, a.xmap_in, line, n)];
         }
     }
@@ -545,7 +551,7 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     if (a.nlines % W) return cudaErrorInvalidValue;
     b.pf_groups = (a.pf_groups > 0 && (a.nlines / W) * C > 2 * a.pf_groups) ? (a.pf_groups + C - 1) / C : 0;   // CTAs -> groups
     if constexpr (C > 1) {
-        if (!(a.variant & (COL ? 1 : 2))) {
+        if (COL ? !(a.variant & 1) : (a.deint_out != 0)) {
             if (a.variant & 4) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, false>, b);
             return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, true>, b);
         }

@@ -604,6 +604,19 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_qpsi_sum(const cd* __restr
     block_reduce_store<1>(s, partials);
 }
 
+// Physical arrays of a grid whose row pass is split over a cluster of C CTAs (N = 8192: C = 2) are stored with x
+// de-interleaved: position p of a row holds x = C*(p % M) + p / M (M = N/C).  All physical-space kernels are
+// pointwise, so only uploads (set_q, set_phi, set_c, fft2) and downloads (attribute reads) convert.
+template <typename T>
+__global__ void k_deint(const T* __restrict__ in, T* __restrict__ out, size_t total, int N, int M, int C, int to_deint) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / N;
+        const int p = (int)(i % N), x = C * (p % M) + p / M;
+        if (to_deint) out[row * N + p] = in[row * N + x];
+        else out[row * N + x] = in[row * N + p];
+    }
+}
+
 // split / merge helpers for attribute reads and seeding
 __global__ void k_extract_real(const cd* __restrict__ in, double* __restrict__ out, size_t n, int which) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

@@ -64,6 +64,7 @@ struct niwqg_handle {
     double *part = nullptr, *sumsD = nullptr, *sumsE = nullptr, *sumsX = nullptr, *sumsI = nullptr, *scal = nullptr,
            *stagev = nullptr;
     bool q_set = false, phi_set = false;
+    int deintC = 1, deintM = 0;   // physical x order: de-interleaved mod deintC when the row pass is a cluster (k_deint)
     // slab decomposition over nranks GPUs (one process per GPU): physical arrays hold nyl = N/P rows, spectral
     // arrays all N rows of ncl = N/P columns (Grid, common.cuh); each 2-D transform = local pass, NCCL all-to-all,
     // local pass
@@ -199,6 +200,7 @@ static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.variant = h->fft_variant;
     a.g = h->g;
     a.xmap_in = a.xmap_out = 0;
+    a.deint_in = a.deint_out = 0;
     a.xchunk = h->nyl * h->ncl;
     a.mstride = h->npts;
     a.pitch = h->ncl;
@@ -218,7 +220,9 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         // pass 1: rows
         a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->N;
         a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+        a.deint_in = (!inverse && h->deintC > 1); a.deint_out = (inverse && h->deintC > 1);   // the x side of the row pass
         { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
+        a.deint_in = a.deint_out = 0;
         // pass 2: columns
         a.in = out; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col; a.nlines = h->N;
         a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
@@ -240,8 +244,9 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         a.nyl_shift = sh;
         a.in = in; a.out = nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0; a.conj_out = 0;
         if (!inverse) {
-            a.tw = h->tw_row; a.nlines = h->nyl; a.conj_in = 0;
+            a.tw = h->tw_row; a.nlines = h->nyl; a.conj_in = 0; a.deint_in = (h->deintC > 1);
             { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+            a.deint_in = 0;
         } else {
             a.tw = h->tw_col; a.nlines = h->ncl; a.conj_in = 1;
             { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
@@ -254,6 +259,7 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
             { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
         } else {
             a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
+            a.deint_out = (h->deintC > 1);
             { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
         }
         h->launches += 3;
@@ -261,8 +267,9 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     }
     if (!inverse) {
         a.in = in; a.out = h->X; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_out = 1;
-        a.conj_in = 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+        a.conj_in = 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0; a.deint_in = (h->deintC > 1);
         { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+        a.deint_in = 0;
         int r = slab_all_to_all(h, h->X, h->Y);
         if (r) return r;
         a.in = h->Y; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col; a.nlines = h->ncl; a.xmap_out = 0;
@@ -274,6 +281,7 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         int r = slab_all_to_all(h, h->X, h->Y);
         if (r) return r;
         a.in = h->Y; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1;
+        a.deint_out = (h->deintC > 1);
         a.conj_in = 0; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
         { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
     }
@@ -374,7 +382,9 @@ static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
 }
 
 // _invert + _calc_rel_vorticity + (u,v) for the current (qh, phi, phix, phiy)
-static int invert_family(niwqg_handle* h) {
+// keep_qwh: store the wave-PV spectrum qwh (only diagnostics and attribute reads use it: the step itself carries it
+// inside the packed q + i qw spectrum), so the stages that are overwritten before anyone can look skip the write
+static int invert_family(niwqg_handle* h, bool keep_qwh = true) {
     InvertArgs ia{};
     ia.g = h->g;
     ia.flags = h->flags; ia.f = h->p.f; ia.qh = h->qh[h->cq]; ia.filtr = h->filtr;
@@ -384,7 +394,7 @@ static int invert_family(niwqg_handle* h) {
         CK(cudaGetLastError());
         h->launches++;
         FFT(h->W, h->W, false, PRO_NONE, h->B);
-        ia.W = h->W; ia.qwh = h->qwh; ia.inv_jscale = 1.0 / h->jscale;
+        ia.W = h->W; ia.qwh = keep_qwh ? h->qwh : nullptr; ia.inv_jscale = 1.0 / h->jscale;
     }
     if (h->flags & MF_YBJ) ia.uvgen = h->uv;
     ia.partials = (h->flags & MF_YBJ) ? nullptr : h->part;
@@ -483,7 +493,7 @@ static int step_family(niwqg_handle* h) {
             const bool grad = (h->flags & MF_WAVE_PV) != 0;   // only jacobian_phic_phi refreshes phix, phiy (F6)
             int r = wave_fields(h, true, grad, !(h->flags & MF_SPEC_BUDGET));
             if (r) return r;
-            r = invert_family(h);
+            r = invert_family(h, st == 4);
             if (r) return r;
         }
     }
@@ -578,6 +588,33 @@ static int qg_gamma_c(niwqg_handle* h) {
 }
 
 // ---------------------------------------------------------------------------
+// physical arrays cross the ABI in natural x order; on the device they may be de-interleaved (k_deint)
+// ---------------------------------------------------------------------------
+template <typename T>
+static int upload_phys(niwqg_handle* h, const void* src, T* dst, size_t nelem, int on_device) {
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (h->deintC <= 1) { CK(cudaMemcpyAsync(dst, src, nelem * sizeof(T), kind, h->stream)); return 0; }
+    T* stage = (T*)h->P2;
+    CK(cudaMemcpyAsync(stage, src, nelem * sizeof(T), kind, h->stream));
+    k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(stage, dst, nelem, h->N, h->deintM, h->deintC, 1);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+template <typename T>
+static int download_phys(niwqg_handle* h, const T* src, void* dst, size_t nelem, int on_device, T* stage) {
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (h->deintC > 1) {
+        k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(src, stage, nelem, h->N, h->deintM, h->deintC, 0);
+        CK(cudaGetLastError());
+        h->launches++;
+        src = stage;
+    }
+    CK(cudaMemcpyAsync(dst, src, nelem * sizeof(T), kind, h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
 extern "C" {
@@ -618,6 +655,9 @@ static int create_impl(niwqg_handle* h) {
     h->nk = h->qg ? N / 2 + 1 : h->ncl;
     h->npts = (size_t)h->nyl * N; h->nspec = (size_t)N * h->nk;
     h->Mg = (double)N * (double)N;
+    // de-interleaved physical x order (row pass = push kernel with contiguous stores): correct, but measured slower
+    // than the pull kernel on the natural layout (0.578 vs 0.535 ms per 8192^2 row pass), so it is opt-in
+    if (N > NIWQG_ROW_MAXM && getenv("NIWQG_DEINT")) { h->deintM = NIWQG_ROW_MAXM; h->deintC = N / NIWQG_ROW_MAXM; }
     h->g = Grid{N, 2.0 * M_PI / p.L, h->ncl, h->ncl / 2, h->rank, h->nranks > 1 ? 1 : 0};
     if (h->nranks > 1) {
         int r = nccl_load(h->err);
@@ -812,8 +852,7 @@ __global__ void k_set_scalar_from_sum(double* scal, int slot, const double* sums
 int niwqg_set_q(niwqg_handle* h, const double* q, int on_device) {
     CK(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->B * h->npts;
-    CK(cudaMemcpyAsync(h->rscratch, q, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                       h->stream));
+    { int r0 = upload_phys<double>(h, q, h->rscratch, n, on_device); if (r0) return r0; }
     const double M2 = h->Mg * h->Mg;
     if (h->qg) {
         // qh = rfft2(q): full c2c of the real field, keep columns 0..N/2 (QGModel.py:516-518)
@@ -885,8 +924,7 @@ int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
     if (h->qg) { h->err = "set_phi: QGModel has no wave field"; return -1; }
     CK(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->B * h->npts;
-    CK(cudaMemcpyAsync(h->phi, phi, n * sizeof(cd), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                       h->stream));
+    { int r0 = upload_phys<cd>(h, phi, h->phi, n, on_device); if (r0) return r0; }
     FFT(h->phi, h->phih[h->cp], false, PRO_NONE, h->B);
     int r = pe_niw_refresh(h, h->sumsX);
     if (r) return r;
@@ -912,8 +950,7 @@ int niwqg_set_c(niwqg_handle* h, const double* c, int on_device) {
     if (!h->qg || !h->p.passive_scalar) { h->err = "set_c: needs QGModel(passive_scalar=True)"; return -1; }
     CK(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->B * h->npts;
-    CK(cudaMemcpyAsync(h->rscratch, c, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                       h->stream));
+    { int r0 = upload_phys<double>(h, c, h->rscratch, n, on_device); if (r0) return r0; }
     FFT(h->rscratch, h->W, false, PRO_REAL_IN, h->B);
     k_qg_take_half<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->W, h->chh[h->cc], h->N, h->nk);
     CK(cudaGetLastError());
@@ -1250,7 +1287,17 @@ int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t by
     }
     if (r) return r;
     if (!src) { h->err = "get_field: field not defined for this model"; return -1; }
-    CK(cudaMemcpyAsync(dst, src, bytes, kind, h->stream));
+    switch (field) {   // physical fields leave in natural x order
+        case NIWQG_F_Q: case NIWQG_F_QW: case NIWQG_F_QPSI: case NIWQG_F_U: case NIWQG_F_V: case NIWQG_F_C: case NIWQG_F_P:
+            r = download_phys<double>(h, (const double*)src, dst, h->npts, on_device, (double*)h->P2);
+            break;
+        case NIWQG_F_PHI: case NIWQG_F_PHIX: case NIWQG_F_PHIY: case NIWQG_F_LAPPHI:
+            r = download_phys<cd>(h, (const cd*)src, dst, h->npts, on_device, h->P2);
+            break;
+        default:
+            CK(cudaMemcpyAsync(dst, src, bytes, kind, h->stream));
+    }
+    if (r) return r;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1262,14 +1309,18 @@ int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
     if (h->nranks > 1 && (kind == NIWQG_FFT_R2C || kind == NIWQG_FFT_C2R)) { h->err = "fft2: half-spectrum kinds are single-GPU only"; return -1; }
     switch (kind) {
         case NIWQG_FFT_C2C_FWD:
+            { int r0 = upload_phys<cd>(h, in, h->P1, h->npts, 0); if (r0) return r0; }
+            FFT(h->P1, h->P1, false, PRO_NONE, 1);
+            CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
+            break;
         case NIWQG_FFT_C2C_INV:
             CK(cudaMemcpyAsync(h->P1, in, c, cudaMemcpyHostToDevice, h->stream));
-            FFT(h->P1, h->P1, kind == NIWQG_FFT_C2C_INV, PRO_NONE, 1);
-            CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
+            FFT(h->P1, h->P1, true, PRO_NONE, 1);
+            { int r0 = download_phys<cd>(h, h->P1, out, h->npts, 0, h->P2); if (r0) return r0; }
             break;
         case NIWQG_FFT_R2C_FULL:
         case NIWQG_FFT_R2C:
-            CK(cudaMemcpyAsync(h->rscratch, in, r, cudaMemcpyHostToDevice, h->stream));
+            { int r0 = upload_phys<double>(h, in, h->rscratch, h->npts, 0); if (r0) return r0; }
             FFT(h->rscratch, h->P1, false, PRO_REAL_IN, 1);
             if (kind == NIWQG_FFT_R2C_FULL)
                 CK(cudaMemcpyAsync(out, h->P1, c, cudaMemcpyDeviceToHost, h->stream));
@@ -1285,7 +1336,7 @@ int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
             CK(cudaGetLastError());
             h->launches++;
             FFT(h->P1, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);
-            CK(cudaMemcpyAsync(out, h->rscratch, r, cudaMemcpyDeviceToHost, h->stream));
+            { int r0 = download_phys<double>(h, h->rscratch, out, h->npts, 0, (double*)h->P2); if (r0) return r0; }
         } break;
         default: h->err = "fft2: unknown kind"; return -1;
     }
