@@ -190,7 +190,7 @@ class Handle(object):
             pass
 
     # -- slab: fused exchange over peer memory ------------------------------
-    IPC_BYTES = 128
+    IPC_BYTES = 256      # 2 lanes x 2 receive buffers x 64-byte cudaIpcMemHandle_t
 
     def ipc_export(self):
         buf = C.create_string_buffer(self.IPC_BYTES)

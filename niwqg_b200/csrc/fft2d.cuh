@@ -70,6 +70,8 @@ struct FftArgs {
     int nyl_shift;    // log2(rows per rank)
     cd* peer[8];      // receive buffer of every rank (peer[rank] = own), CUDA-IPC mapped
     size_t mstride;   // elements between ensemble members
+    int one_cta_per_sm;   // request enough shared memory that only ONE CTA of this launch fits on an SM: leaves the other
+                      // half of every SM to the pass that runs concurrently on the other lane (slab overlap)
     int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel;
                       // bit 2 = the push kernel uses plain remote stores + a cluster barrier instead of st.async
 };
@@ -522,15 +524,17 @@ template <int N, bool COL>
 static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     constexpr int M = PassCfg<N, COL>::M, W = PassCfg<N, COL>::W, C = PassCfg<N, COL>::C;
     using TL = Tile<M, W, C, COL>;
+    constexpr size_t HALF_SM = 116 * 1024;      // more than half of the 227 KB an SM can give to CTAs
+    constexpr size_t SMEM_MAX = TL::SMEM > HALF_SM ? TL::SMEM : HALF_SM;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_fft_pass<M, W, C, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)TL::SMEM);
+                                             (int)SMEM_MAX);
         if (e != cudaSuccess) return e;
         if constexpr (C > 1) {
-            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
             if (e != cudaSuccess) return e;
         }
         attr_set = true;
@@ -538,7 +542,7 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((a.nlines / W) * C, batch, 1);
     cfg.blockDim = dim3(TL::T, 1, 1);
-    cfg.dynamicSmemBytes = TL::SMEM;
+    cfg.dynamicSmemBytes = (a.one_cta_per_sm && TL::SMEM < HALF_SM) ? HALF_SM : TL::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;

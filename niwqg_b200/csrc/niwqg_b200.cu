@@ -73,11 +73,24 @@ struct niwqg_handle {
     double Mg = 0;              // N*N of the GLOBAL grid (mean denominators)
     cd *X = nullptr, *Y = nullptr;   // all-to-all send / receive buffers (NCCL path)
     // fused path: passes push straight into the peers' receive buffers (CUDA IPC), double-buffered per transform
-    cd* Yp[2] = {nullptr, nullptr};
-    cd* peerY[2][8] = {};
+    // Two LANES (stream + communicator + receive buffers each): independent transforms of one group (phi/phix/phiy,
+    // u+iv / q+iqw, the two RHS products) alternate between them, so one transform's NVLink-bound pushing pass
+    // overlaps another's HBM-bound local pass.  Lane 0 is the handle's main stream.
+    static constexpr int NLANE = 2;
+    cd* Yp[NLANE][2] = {};
+    cd* peerY[NLANE][2][8] = {};
     bool p2p = false;
-    int ybuf = 0;
-    double* bar = nullptr;      // 1-element all-reduce buffer: the cross-GPU barrier between the two passes
+    int ybuf[NLANE] = {0, 0};
+    double* bar[NLANE] = {nullptr, nullptr};   // 1-element all-reduce buffers: the cross-GPU barrier between passes
+    cudaStream_t lane_stream[NLANE] = {nullptr, nullptr};
+    ncclComm_t lane_comm[NLANE] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool lanes = false;         // second lane usable
+    bool in_group = false;      // inside fft2_group with both lanes active
+    int group_occ_limit = 0;    // 1: passes of a two-lane group run one CTA per SM (measured slower: off)
+    int exchange = 0;           // 0: pushes fused into the first pass; 1: first pass writes the exchange layout locally,
+                                // the copy engines move the chunks to the peers (no SM involved, overlaps the other lane)
+    cd* Xl[NLANE] = {nullptr, nullptr};   // per-lane send staging of the copy-engine exchange
     ncclComm_t comm = nullptr;
     int fft_variant = 6;        // FftArgs::variant: column clusters push (DIF, plain remote stores), row clusters pull (DIT):
                                 // measured best (profiles/r01b_cluster_variants.txt, r01d_async_push.txt)
@@ -103,13 +116,14 @@ static cudaEvent_t prof_event(niwqg_handle* h) {
 struct ProfScope {
     niwqg_handle* h; int kind; cudaEvent_t a;
     ProfScope(niwqg_handle* h_, int k) : h(h_), kind(k), a(nullptr) {
-        if (h->prof) { a = prof_event(h); cudaEventRecord(a, h->stream); }
+        if (h->prof && kind >= 0) { a = prof_event(h); cudaEventRecord(a, h->stream); }
     }
     ~ProfScope() {
-        if (h->prof) { cudaEvent_t b = prof_event(h); cudaEventRecord(b, h->stream); h->prof_recs.push_back({kind, a, b}); }
+        if (h->prof && kind >= 0) { cudaEvent_t b = prof_event(h); cudaEventRecord(b, h->stream); h->prof_recs.push_back({kind, a, b}); }
     }
 };
 #define PROF(kind) ProfScope prof_scope__(h, kind)
+#define PROF_ON(kind, lane) ProfScope prof_scope__(h, (lane) == 0 ? (kind) : -1)
 
 // ---------------------------------------------------------------------------
 static int dalloc(niwqg_handle* h, void** p, size_t bytes, bool zero = true) {
@@ -144,6 +158,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -164,7 +179,7 @@ static int nccl_load(std::string& err) {
     NIWQG_SYM(GetUniqueId, "ncclGetUniqueId") NIWQG_SYM(CommInitRank, "ncclCommInitRank")
     NIWQG_SYM(CommDestroy, "ncclCommDestroy") NIWQG_SYM(AllReduce, "ncclAllReduce") NIWQG_SYM(Send, "ncclSend")
     NIWQG_SYM(Recv, "ncclRecv") NIWQG_SYM(GroupStart, "ncclGroupStart") NIWQG_SYM(GroupEnd, "ncclGroupEnd")
-    NIWQG_SYM(GetErrorString, "ncclGetErrorString")
+    NIWQG_SYM(GetErrorString, "ncclGetErrorString") NIWQG_SYM(CommSplit, "ncclCommSplit")
 #undef NIWQG_SYM
     g_nccl.lib = lib;
     return 0;
@@ -201,6 +216,7 @@ static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.g = h->g;
     a.xmap_in = a.xmap_out = 0;
     a.deint_in = a.deint_out = 0;
+    a.one_cta_per_sm = 0;
     a.xchunk = h->nyl * h->ncl;
     a.mstride = h->npts;
     a.pitch = h->ncl;
@@ -211,7 +227,7 @@ static void fft_common_args(niwqg_handle* h, FftArgs& a) {
 // (columns are local); inverse = column pass -> all-to-all -> row pass.  The spectral prologue multiply and the
 // conjugation of an inverse transform ride on whichever pass comes first, conj + 1/N^2 on the last.
 static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro, int batch, int epi = EPI_NONE,
-                void* real_out = nullptr) {
+                void* real_out = nullptr, int lane = 0) {
     FftArgs a{};
     fft_common_args(h, a);
     const double sc = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
@@ -233,34 +249,50 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     }
     if (batch != 1) { h->err = "slab transforms take one member"; return -1; }
     if (h->p2p) {
+        cudaStream_t st = h->lane_stream[lane];
+        a.one_cta_per_sm = h->in_group ? h->group_occ_limit : 0;
         // fused exchange: the first pass stores into the owners' receive buffers over NVLink; one tiny all-reduce is
         // the barrier that says "everybody's pushes have landed"; the second pass reads the local receive buffer.
-        const int b = h->ybuf;
-        h->ybuf ^= 1;     // the peers may still be reading the other buffer (previous transform's second pass)
-        a.push = 1;
-        for (int r = 0; r < h->nranks; ++r) a.peer[r] = h->peerY[b][r];
+        const int b = h->ybuf[lane];
+        h->ybuf[lane] ^= 1;     // the peers may still be reading the other buffer (previous transform's second pass)
+        const bool ce = h->exchange == 1;
+        a.push = ce ? 0 : 1;
+        for (int r = 0; r < h->nranks; ++r) a.peer[r] = h->peerY[lane][b][r];
         int sh = 0;
         while ((1 << sh) < h->nyl) ++sh;
         a.nyl_shift = sh;
-        a.in = in; a.out = nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0; a.conj_out = 0;
+        a.in = in; a.out = ce ? (void*)h->Xl[lane] : nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0;
+        a.conj_out = 0;
         if (!inverse) {
-            a.tw = h->tw_row; a.nlines = h->nyl; a.conj_in = 0; a.deint_in = (h->deintC > 1);
-            { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
-            a.deint_in = 0;
+            a.tw = h->tw_row; a.nlines = h->nyl; a.conj_in = 0; a.deint_in = (h->deintC > 1); a.xmap_out = ce ? 1 : 0;
+            { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, 1, st)); }
+            a.deint_in = 0; a.xmap_out = 0;
         } else {
             a.tw = h->tw_col; a.nlines = h->ncl; a.conj_in = 1;
-            { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
+            { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, 1, st)); }
         }
-        { PROF(PK_COMM); NK(g_nccl.AllReduce(h->bar, h->bar, 1, ncclDouble, ncclSum, h->comm, h->stream)); }
+        {
+            PROF_ON(PK_COMM, lane);
+            if (ce) {
+                // chunk r of the send staging -> chunk [my rank] of rank r's receive buffer, by the copy engines
+                const size_t chunk = (size_t)h->nyl * h->ncl;
+                for (int k = 0; k < h->nranks; ++k) {
+                    const int r = (h->rank + k) % h->nranks;          // start with my own chunk, then ring order
+                    CK(cudaMemcpyAsync(h->peerY[lane][b][r] + (size_t)h->rank * chunk, h->Xl[lane] + (size_t)r * chunk,
+                                       chunk * sizeof(cd), cudaMemcpyDeviceToDevice, st));
+                }
+            }
+            NK(g_nccl.AllReduce(h->bar[lane], h->bar[lane], 1, ncclDouble, ncclSum, h->lane_comm[lane], st));
+        }
         a.push = 0;
-        a.in = h->Yp[b]; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.conj_in = 0;
+        a.in = h->Yp[lane][b]; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.conj_in = 0;
         if (!inverse) {
             a.tw = h->tw_col; a.nlines = h->ncl;
-            { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, 1, h->stream)); }
+            { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, 1, st)); }
         } else {
             a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
             a.deint_out = (h->deintC > 1);
-            { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, 1, h->stream)); }
+            { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, 1, st)); }
         }
         h->launches += 3;
         return 0;
@@ -293,6 +325,28 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         int r__ = fft2(h, __VA_ARGS__);   \
         if (r__) return r__;              \
     } while (0)
+
+// A group of mutually independent transforms (same or different inputs, distinct outputs).  Slab runs with the fused
+// exchange alternate them between the two lanes; everything else runs them back to back on the main stream.
+struct FftJob { const void* in; cd* out; bool inverse; int pro; };
+static int fft2_group(niwqg_handle* h, const FftJob* jobs, int n) {
+    const bool par = h->lanes && h->p2p && !h->prof && n > 1;
+    if (!par) {
+        for (int i = 0; i < n; ++i) FFT(jobs[i].in, jobs[i].out, jobs[i].inverse, jobs[i].pro, h->B);
+        return 0;
+    }
+    CK(cudaEventRecord(h->ev_fork, h->lane_stream[0]));
+    CK(cudaStreamWaitEvent(h->lane_stream[1], h->ev_fork, 0));
+    h->in_group = true;
+    for (int i = 0; i < n; ++i) {
+        int r = fft2(h, jobs[i].in, jobs[i].out, jobs[i].inverse, jobs[i].pro, h->B, EPI_NONE, nullptr, i & 1);
+        if (r) { h->in_group = false; return r; }
+    }
+    h->in_group = false;
+    CK(cudaEventRecord(h->ev_join, h->lane_stream[1]));
+    CK(cudaStreamWaitEvent(h->lane_stream[0], h->ev_join, 0));
+    return 0;
+}
 
 static int finalize(niwqg_handle* h, int K, double* out, int is_max = 0) {
     PROF(PK_SMALL);
@@ -369,16 +423,18 @@ static BudgetArgs budget_args(niwqg_handle* h, int stage) {
 // phi-derived physical fields from the current phih: phi, lapphi (+lap2phi) always; phix, phiy when `grad`
 static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
     const cd* ph = h->phih[h->cp];
-    if (want_phi) FFT(ph, h->phi, true, PRO_NONE, h->B);
+    FftJob jobs[5];
+    int n = 0;
+    if (want_phi) jobs[n++] = FftJob{ph, h->phi, true, PRO_NONE};
     if (grad) {
-        FFT(ph, h->phix, true, PRO_IK, h->B);
-        FFT(ph, h->phiy, true, PRO_IL, h->B);
+        jobs[n++] = FftJob{ph, h->phix, true, PRO_IK};
+        jobs[n++] = FftJob{ph, h->phiy, true, PRO_IL};
     }
     if (lap) {
-        FFT(ph, h->lapphi, true, PRO_NEG_WV2, h->B);
-        if (h->flags & MF_HAS_LAP2) FFT(ph, h->lap2phi, true, PRO_WV4, h->B);
+        jobs[n++] = FftJob{ph, h->lapphi, true, PRO_NEG_WV2};
+        if (h->flags & MF_HAS_LAP2) jobs[n++] = FftJob{ph, h->lap2phi, true, PRO_WV4};
     }
-    return 0;
+    return fft2_group(h, jobs, n);
 }
 
 // _invert + _calc_rel_vorticity + (u,v) for the current (qh, phi, phix, phiy)
@@ -405,8 +461,9 @@ static int invert_family(niwqg_handle* h, bool keep_qwh = true) {
     if (h->flags & MF_YBJ) {
         FFT(h->uv, h->uv, true, PRO_NONE, h->B);
     } else {
-        FFT(h->ph, h->uv, true, PRO_UV, h->B);
-        FFT(h->qs, h->qs, true, PRO_NONE, h->B);
+        const FftJob jobs[2] = {FftJob{h->ph, h->uv, true, PRO_UV}, FftJob{h->qs, h->qs, true, PRO_NONE}};
+        int r = fft2_group(h, jobs, 2);
+        if (r) return r;
     }
     return 0;
 }
@@ -436,8 +493,9 @@ static int step_family(niwqg_handle* h) {
     for (int st = 1; st <= 4; ++st) {
         if (ybj) {   // _calc_grad_phi from the stage's phih (YBJModel.py:135-139); phi stays stale (F7)
             const cd* cur = (st == 1) ? h->phih[op] : h->phih[np];
-            FFT(cur, h->phix, true, PRO_IK, h->B);
-            FFT(cur, h->phiy, true, PRO_IL, h->B);
+            const FftJob jobs[2] = {FftJob{cur, h->phix, true, PRO_IK}, FftJob{cur, h->phiy, true, PRO_IL}};
+            int r = fft2_group(h, jobs, 2);
+            if (r) return r;
         }
         StageArgs sa{};
         sa.g = h->g;
@@ -453,9 +511,12 @@ static int step_family(niwqg_handle* h) {
             h->launches++;
             if (!ybj) {
                 FIN(SD_COUNT, h->sumsD);
-                FFT(h->P1, h->P1, false, PRO_NONE, h->B);
+                const FftJob jobs[2] = {FftJob{h->P1, h->P1, false, PRO_NONE}, FftJob{h->P2, h->P2, false, PRO_NONE}};
+                int r = fft2_group(h, jobs, 2);
+                if (r) return r;
+            } else {
+                FFT(h->P2, h->P2, false, PRO_NONE, h->B);
             }
-            FFT(h->P2, h->P2, false, PRO_NONE, h->B);
             { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
             CK(cudaGetLastError());
             h->launches++;
@@ -625,11 +686,17 @@ int niwqg_destroy(niwqg_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->lane_stream[1]) cudaStreamSynchronize(h->lane_stream[1]);
     if (h->p2p)
         for (int r = 0; r < h->nranks; ++r)
-            for (int b = 0; b < 2; ++b)
-                if (r != h->rank && h->peerY[b][r]) cudaIpcCloseMemHandle(h->peerY[b][r]);
+            for (int l = 0; l < niwqg_handle::NLANE; ++l)
+                for (int b = 0; b < 2; ++b)
+                    if (r != h->rank && h->peerY[l][b][r]) cudaIpcCloseMemHandle(h->peerY[l][b][r]);
+    if (h->lane_comm[1] && g_nccl.CommDestroy) g_nccl.CommDestroy(h->lane_comm[1]);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->lane_stream[1]) cudaStreamDestroy(h->lane_stream[1]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -742,7 +809,22 @@ static int create_impl(niwqg_handle* h) {
     DA(h->qh[0], ssz); DA(h->ph, ssz); DA(h->uv, fsz); DA(h->qs, fsz);
     DA(h->P1, fsz); DA(h->P2, fsz); DA(h->W, fsz);
     DA(h->rscratch, B * h->npts * sizeof(double));
-    if (h->nranks > 1) { DA(h->X, fsz); DA(h->Y, fsz); DA(h->Yp[0], fsz); DA(h->Yp[1], fsz); DA(h->bar, 64); }
+    h->lane_stream[0] = h->stream;
+    h->lane_comm[0] = h->comm;
+    if (h->nranks > 1) {
+        DA(h->X, fsz); DA(h->Y, fsz);
+        const int nl = getenv("NIWQG_ONE_LANE") ? 1 : niwqg_handle::NLANE;
+        if (const char* e = getenv("NIWQG_GROUP_OCC_LIMIT")) h->group_occ_limit = atoi(e);
+        for (int l = 0; l < nl; ++l) { DA(h->Yp[l][0], fsz); DA(h->Yp[l][1], fsz); DA(h->bar[l], 64); DA(h->Xl[l], fsz); }
+        if (const char* e = getenv("NIWQG_SLAB_EXCHANGE")) h->exchange = (strcmp(e, "ce") == 0) ? 1 : 0;
+        if (nl > 1) {
+            CK(cudaStreamCreateWithFlags(&h->lane_stream[1], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+            NK(g_nccl.CommSplit(h->comm, 0, h->rank, &h->lane_comm[1], nullptr));
+            h->lanes = true;
+        }
+    }
     if (p.model != NIWQG_MODEL_YBJ) { DA(h->qh[1], ssz); DA(h->y1q, ssz); DA(h->F0q, ssz); DA(h->Fabq, ssz); }
     if (!h->qg) {
         DA(h->phih[0], ssz); DA(h->phih[1], ssz); DA(h->y1p, ssz); DA(h->F0p, ssz); DA(h->Fabp, ssz);
@@ -798,14 +880,18 @@ int niwqg_nccl_unique_id(char* out128) {
 }
 
 int niwqg_ipc_export(niwqg_handle* h, char* out, size_t bytes) {
-    if (bytes < 2 * sizeof(cudaIpcMemHandle_t)) { h->err = "ipc_export: buffer too small"; return -1; }
+    const int nb = niwqg_handle::NLANE * 2;
+    if (bytes < nb * sizeof(cudaIpcMemHandle_t)) { h->err = "ipc_export: buffer too small"; return -1; }
     if (h->nranks <= 1) { h->err = "ipc_export: not a slab handle"; return -1; }
     CK(cudaSetDevice(h->p.device));
-    for (int b = 0; b < 2; ++b) {
-        cudaIpcMemHandle_t mh;
-        CK(cudaIpcGetMemHandle(&mh, h->Yp[b]));
-        memcpy(out + b * sizeof mh, &mh, sizeof mh);
-    }
+    memset(out, 0, bytes);
+    for (int l = 0; l < niwqg_handle::NLANE; ++l)
+        for (int b = 0; b < 2; ++b) {
+            if (!h->Yp[l][b]) continue;
+            cudaIpcMemHandle_t mh;
+            CK(cudaIpcGetMemHandle(&mh, h->Yp[l][b]));
+            memcpy(out + (l * 2 + b) * sizeof mh, &mh, sizeof mh);
+        }
     return 0;
 }
 
@@ -813,14 +899,16 @@ int niwqg_ipc_import(niwqg_handle* h, const char* all, size_t bytes_per_rank) {
     if (h->nranks <= 1 || h->nranks > 8) { h->err = "ipc_import: 2..8 ranks"; return -1; }
     CK(cudaSetDevice(h->p.device));
     for (int r = 0; r < h->nranks; ++r)
-        for (int b = 0; b < 2; ++b) {
-            if (r == h->rank) { h->peerY[b][r] = h->Yp[b]; continue; }
-            cudaIpcMemHandle_t mh;
-            memcpy(&mh, all + (size_t)r * bytes_per_rank + b * sizeof mh, sizeof mh);
-            void* ptr = nullptr;
-            CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
-            h->peerY[b][r] = (cd*)ptr;
-        }
+        for (int l = 0; l < niwqg_handle::NLANE; ++l)
+            for (int b = 0; b < 2; ++b) {
+                if (!h->Yp[l][b]) continue;
+                if (r == h->rank) { h->peerY[l][b][r] = h->Yp[l][b]; continue; }
+                cudaIpcMemHandle_t mh;
+                memcpy(&mh, all + (size_t)r * bytes_per_rank + (l * 2 + b) * sizeof mh, sizeof mh);
+                void* ptr = nullptr;
+                CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+                h->peerY[l][b][r] = (cd*)ptr;
+            }
     h->p2p = true;
     return 0;
 }
