@@ -237,13 +237,13 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->N;
         a.conj_in = inverse ? 1 : 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
         a.deint_in = (!inverse && h->deintC > 1); a.deint_out = (inverse && h->deintC > 1);   // the x side of the row pass
-        { PROF(PK_FFT_ROW); CK(launch_pass<false>(h->N, a, batch, h->stream)); }
+        { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, batch, h->lane_stream[lane])); }
         a.deint_in = a.deint_out = 0;
         // pass 2: columns
         a.in = out; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col; a.nlines = h->N;
         a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
         a.scale = sc; a.scale_im = inverse ? -sc : sc;
-        { PROF(PK_FFT_COL); CK(launch_pass<true>(h->N, a, batch, h->stream)); }
+        { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, batch, h->lane_stream[lane])); }
         h->launches += 2;
         return 0;
     }
@@ -330,7 +330,8 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
 // exchange alternate them between the two lanes; everything else runs them back to back on the main stream.
 struct FftJob { const void* in; cd* out; bool inverse; int pro; };
 static int fft2_group(niwqg_handle* h, const FftJob* jobs, int n) {
-    const bool par = h->lanes && h->p2p && !h->prof && n > 1;
+    // (one GPU: the column pass of one transform, bound by the DSMEM exchange, runs next to the row pass of the other)
+    const bool par = h->lanes && (h->p2p || h->nranks == 1) && !h->prof && n > 1;
     if (!par) {
         for (int i = 0; i < n; ++i) FFT(jobs[i].in, jobs[i].out, jobs[i].inverse, jobs[i].pro, h->B);
         return 0;
@@ -811,6 +812,12 @@ static int create_impl(niwqg_handle* h) {
     DA(h->rscratch, B * h->npts * sizeof(double));
     h->lane_stream[0] = h->stream;
     h->lane_comm[0] = h->comm;
+    if (h->nranks == 1 && !getenv("NIWQG_ONE_LANE")) {
+        CK(cudaStreamCreateWithFlags(&h->lane_stream[1], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        h->lanes = true;
+    }
     if (h->nranks > 1) {
         DA(h->X, fsz); DA(h->Y, fsz);
         const int nl = getenv("NIWQG_ONE_LANE") ? 1 : niwqg_handle::NLANE;
