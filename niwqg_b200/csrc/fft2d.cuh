@@ -269,7 +269,6 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     // stage twiddles -> shared memory: L1 is invalidated by every cluster-scope acquire on this SM, and a global
     // twiddle load sits on the critical path of every stage
     cd* smtw = smem + (size_t)W * TL::LINE;
-    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
     cd v[fftc::E];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
     // all 16 loads are issued back to back (nothing between them depends on loaded data); the prologue multiply and
@@ -291,6 +290,8 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
             v[e] = in[fft_index<N, COL>(a, a.xmap_in, line, n)];
         }
     }
+    // stage twiddles -> shared memory, AFTER the data loads are out (this store waits for its own global load)
+    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
 #define NIWQG_PRO_CASE(P)                                                                     \
     case P:                                                                                   \
         _Pragma("unroll") for (int e = 0; e < fftc::E; ++e) {                                 \
@@ -397,7 +398,6 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
         }
         cluster_arrive_release();          // ... and the loads below are in flight while the peers get here
     }
-    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
     constexpr int PPT = fftc::E / C;                        // radix-C butterflies per thread
     cd v[fftc::E];
@@ -437,6 +437,8 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
         wk[i] = a.twc[m];                                   // w_N^m
         (void)wq; (void)ln;
     }
+    // stage twiddles -> shared memory, AFTER the data loads are out (this store waits for its own global load)
+    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
 #define NIWQG_PRO_CASE(P)                                                                         \
     case P:                                                                                       \
         _Pragma("unroll") for (int i = 0; i < PPT; ++i) {                                         \
