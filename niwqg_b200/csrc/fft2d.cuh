@@ -79,8 +79,10 @@ struct FftArgs {
 // element n of line `line`: offset inside one member's array
 //   column pass: n-th row of local column `line`;  row pass: natural [line][n], or - on the exchange side of a slab
 //   transform - [owner(n)][line][lc(n)] (the layout ncclAlltoAll moves between the row slabs and the column slabs)
-template <int N, bool COL>
+// NAT: natural single-GPU layout - pitch N, no exchange maps, no pushes: all strides are compile-time constants
+template <int N, bool COL, bool NAT>
 __device__ __forceinline__ size_t fft_index(const FftArgs& a, int xmap, int line, int n) {
+    if (NAT) return COL ? (size_t)n * N + line : (size_t)line * N + n;
     if (COL) return (size_t)n * a.pitch + line;
     if (!xmap) return (size_t)line * N + n;
     int r, lc;
@@ -90,7 +92,7 @@ __device__ __forceinline__ size_t fft_index(const FftArgs& a, int xmap, int line
 // (ky, kx) of element n of line `line` on the spectral side (prologue wavenumbers)
 template <bool COL>
 __device__ __forceinline__ void fft_kykx(const FftArgs& a, int line, int n, int& ky, int& kx) {
-    if (COL) { ky = n; kx = grid_kx(a.g, line); } else { ky = line; kx = n; }
+    if (COL) { ky = n; kx = a.g.sym ? grid_kx(a.g, line) : line; } else { ky = line; kx = n; }
 }
 
 // spectral multiplier of the prologue modes at (row, col) applied to x
@@ -109,11 +111,11 @@ __device__ __forceinline__ cd fft_prologue_one(const FftArgs& a, int row, int co
     return x;
 }
 
-template <int N, bool COL>
+template <int N, bool COL, bool NAT>
 __device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int line, int n, cd x) {
     x.x *= a.scale;
     x.y *= a.scale_im;            // = -scale when the output is conjugated
-    if (a.push) {
+    if (!NAT && a.push) {
         // the all-to-all of a slab transform fused into this pass: the element lands in its owner's receive buffer,
         // chunk [my rank][row within the owner's slab][local column] - exactly what ncclAlltoAll would deliver
         int r;
@@ -129,7 +131,7 @@ __device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int li
         a.peer[r][(size_t)a.g.rank * a.xchunk + off] = x;
         return;
     }
-    const size_t idx = mbase + fft_index<N, COL>(a, a.xmap_out, line, n);
+    const size_t idx = mbase + fft_index<N, COL, NAT>(a, a.xmap_out, line, n);
     if (a.epi == EPI_REAL_OUT) ((double*)a.out)[idx] = x.x;
     else ((cd*)a.out)[idx] = x;
 }
@@ -149,22 +151,22 @@ template <int M, int W, int C, bool COL> struct Tile {
 };
 
 // what happens to the result of the last local stage
-template <int M, int W, int C, bool COL, bool DIF>
+template <int M, int W, int C, bool COL, bool NAT, bool DIF>
 __device__ __forceinline__ void fft_emit(const FftArgs& a, size_t mbase, int line, int w, int c, int k, cd x, cd* smem) {
     using TL = Tile<M, W, C, COL>;
     if constexpr (C == 1) {
-        fft_store<TL::N, COL>(a, mbase, line, k, x);
+        fft_store<TL::N, COL, NAT>(a, mbase, line, k, x);
     } else if constexpr (DIF) {
-        const int n = a.deint_out ? c * M + k : C * k + c;    // decimation in frequency: CTA c produced the outputs
+        const int n = (!NAT && a.deint_out) ? c * M + k : C * k + c;    // decimation in frequency: CTA c produced the outputs
                                                                // congruent to c mod C (stored as one contiguous block
                                                                // when the physical side is de-interleaved)
-        fft_store<TL::N, COL>(a, mbase, line, n, x);
+        fft_store<TL::N, COL, NAT>(a, mbase, line, n, x);
     } else {
         smem[TL::slot(w, k)] = x;   // E_c[k]; the cluster twiddle w_N^{c k} is applied by the gathering CTA
     }
 }
 
-template <int M, int W, int C, bool COL, bool DIF, int NS>
+template <int M, int W, int C, bool COL, bool NAT, bool DIF, int NS>
 __device__ __forceinline__ void fft_stages(cd (&v)[fftc::E], int j, int w, int c, cd* smem, const cd* tw,
                                            const FftArgs& a, int line, size_t mbase) {
     using TL = Tile<M, W, C, COL>;
@@ -177,7 +179,7 @@ __device__ __forceinline__ void fft_stages(cd (&v)[fftc::E], int j, int w, int c
         for (int u = 0; u < S; ++u)
 #pragma unroll
             for (int p = 0; p < R; ++p)
-                fft_emit<M, W, C, COL, DIF>(a, mbase, line, w, c, fftc::stage_out_index<M, NS>(j, u, p), v[u + p * S], smem);
+                fft_emit<M, W, C, COL, NAT, DIF>(a, mbase, line, w, c, fftc::stage_out_index<M, NS>(j, u, p), v[u + p * S], smem);
     } else {
 #pragma unroll
         for (int u = 0; u < S; ++u)
@@ -187,7 +189,7 @@ __device__ __forceinline__ void fft_stages(cd (&v)[fftc::E], int j, int w, int c
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) v[e] = smem[TL::slot(w, j + e * TL::TPF)];
         __syncthreads();
-        fft_stages<M, W, C, COL, DIF, LAST ? NS : NS * R>(v, j, w, c, smem, tw, a, line, mbase);
+        fft_stages<M, W, C, COL, NAT, DIF, LAST ? NS : NS * R>(v, j, w, c, smem, tw, a, line, mbase);
     }
 }
 
@@ -253,7 +255,7 @@ __device__ __forceinline__ void fft_prefetch(const FftArgs& a, int group, int c,
     }
 }
 
-template <int M, int W, int C, bool COL>
+template <int M, int W, int C, bool COL, bool NAT>
 __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pass(FftArgs a) {
     using TL = Tile<M, W, C, COL>;
     constexpr int N = TL::N;
@@ -278,16 +280,16 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) {
             const int m_ = j + e * TL::TPF;
-            const int n = (C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
-            v[e] = make_double2(in[fft_index<N, COL>(a, a.xmap_in, line, n)], 0.0);
+            const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
+            v[e] = make_double2(in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)], 0.0);
         }
     } else {
         const cd* in = (const cd*)a.in + mbase;
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) {
             const int m_ = j + e * TL::TPF;
-            const int n = (C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
-            v[e] = in[fft_index<N, COL>(a, a.xmap_in, line, n)];
+            const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
+            v[e] = in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)];
         }
     }
     // stage twiddles -> shared memory, AFTER the data loads are out (this store waits for its own global load)
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
         for (int e = 0; e < fftc::E; ++e) v[e].y = -v[e].y;
     }
-    fft_stages<M, W, C, COL, false, 1>(v, j, w, c, smem, smtw, a, line, mbase);
+    fft_stages<M, W, C, COL, NAT, false, 1>(v, j, w, c, smem, smtw, a, line, mbase);
     if constexpr (C > 1) {
         // radix-C butterfly across the cluster: this CTA owns k in [c M/C, (c+1) M/C) of every line of the group
         cg::cluster_group cluster = cg::this_cluster();
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
             for (int p = 0; p < C; ++p) {
                 const int n = k + M * fftc::outidx<C>(p);
-                fft_store<N, COL>(a, mbase, ln, n, v[i * C + p]);
+                fft_store<N, COL, NAT>(a, mbase, ln, n, v[i * C + p]);
             }
         }
         cluster_wait_relaxed();     // nobody may exit while a peer still reads its shared memory
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 //   X[C k + q] = FFT_M(Y_q)[k].  No CTA touches a peer's memory after the barrier, so no exit barrier is needed.
 // ASYNC: the pushes are st.async stores crediting the receiver's mbarrier (no producer fence, no cluster rendezvous
 // after the pushes; one cluster barrier at kernel start makes every mbarrier visible before anybody pushes).
-template <int M, int W, int C, bool COL, bool ASYNC>
+template <int M, int W, int C, bool COL, bool NAT, bool ASYNC>
 __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pass_dif(FftArgs a) {
     using TL = Tile<M, W, C, COL>;
     constexpr int N = TL::N;
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
             for (int r = 0; r < C; ++r) {
                 const int n = m + M * r;
-                v[i * C + r] = make_double2(in[fft_index<N, COL>(a, a.xmap_in, ln, n)], 0.0);
+                v[i * C + r] = make_double2(in[fft_index<N, COL, NAT>(a, a.xmap_in, ln, n)], 0.0);
             }
         }
     } else {
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
             for (int r = 0; r < C; ++r) {
                 const int n = m + M * r;
-                v[i * C + r] = in[fft_index<N, COL>(a, a.xmap_in, ln, n)];
+                v[i * C + r] = in[fft_index<N, COL, NAT>(a, a.xmap_in, ln, n)];
             }
         }
     }
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
 #pragma unroll
     for (int e = 0; e < fftc::E; ++e) v[e] = smem[TL::slot(w, j + e * TL::TPF)];
     __syncthreads();
-    fft_stages<M, W, C, COL, true, 1>(v, j, w, c, smem, smtw, a, line, mbase);
+    fft_stages<M, W, C, COL, NAT, true, 1>(v, j, w, c, smem, smtw, a, line, mbase);
 }
 
 // ---- pass geometry: (M, W, C) per grid size
@@ -522,21 +524,21 @@ template <int N, bool COL> struct PassCfg {
     static constexpr int W = (COL && N >= NIWQG_COL_M) ? NIWQG_COL_TILE / M : ((M >= 4096) ? 1 : (M >= 512) ? 4096 / M : 8);
 };
 
-template <int N, bool COL>
-static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
+template <int N, bool COL, bool NAT>
+static cudaError_t launch_pass_g(const FftArgs& a, int batch, cudaStream_t st) {
     constexpr int M = PassCfg<N, COL>::M, W = PassCfg<N, COL>::W, C = PassCfg<N, COL>::C;
     using TL = Tile<M, W, C, COL>;
     constexpr size_t HALF_SM = 116 * 1024;      // more than half of the 227 KB an SM can give to CTAs
     constexpr size_t SMEM_MAX = TL::SMEM > HALF_SM ? TL::SMEM : HALF_SM;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_fft_pass<M, W, C, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_fft_pass<M, W, C, COL, NAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SMEM_MAX);
         if (e != cudaSuccess) return e;
         if constexpr (C > 1) {
-            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, NAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+            e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, NAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
             if (e != cudaSuccess) return e;
         }
         attr_set = true;
@@ -558,11 +560,19 @@ static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     b.pf_groups = (a.pf_groups > 0 && (a.nlines / W) * C > 2 * a.pf_groups) ? (a.pf_groups + C - 1) / C : 0;   // CTAs -> groups
     if constexpr (C > 1) {
         if (COL ? !(a.variant & 1) : (a.deint_out != 0)) {
-            if (a.variant & 4) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, false>, b);
-            return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, true>, b);
+            if (a.variant & 4) return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, NAT, false>, b);
+            return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, NAT, true>, b);
         }
     }
-    return cudaLaunchKernelEx(&cfg, k_fft_pass<M, W, C, COL>, b);
+    return cudaLaunchKernelEx(&cfg, k_fft_pass<M, W, C, COL, NAT>, b);
+}
+
+template <int N, bool COL>
+static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
+    // natural single-GPU geometry gets the kernels with compile-time strides
+    const bool nat = a.pitch == N && !a.push && !a.xmap_in && !a.xmap_out && !a.deint_in && !a.deint_out && !a.g.sym &&
+                     a.mstride == (size_t)N * N;
+    return nat ? launch_pass_g<N, COL, true>(a, batch, st) : launch_pass_g<N, COL, false>(a, batch, st);
 }
 
 // local transform length of a pass (the stage twiddle table to bind)
