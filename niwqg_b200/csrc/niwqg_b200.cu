@@ -86,6 +86,12 @@ struct niwqg_handle {
     ncclComm_t lane_comm[NLANE] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool lanes = false;         // second lane usable
+    // CUDA graphs of one whole step, one per ping-pong parity of the state buffers (key = cq*4 + cp*2 + cc): small grids
+    // are launch-bound (~100 launches of a few microseconds each per step)
+    struct StepGraph { cudaGraphExec_t exec = nullptr; int cq = 0, cp = 0, cc = 0; long long launches = 0; };
+    StepGraph graphs[8];
+    bool use_graphs = false;
+    int direct_steps = 0;       // steps issued without a graph (the first ones set kernel attributes lazily)
     bool in_group = false;      // inside fft2_group with both lanes active
     int group_occ_limit = 0;    // 1: passes of a two-lane group run one CTA per SM (measured slower: off)
     int exchange = 0;           // 0: pushes fused into the first pass; 1: first pass writes the exchange layout locally,
@@ -687,6 +693,7 @@ int niwqg_destroy(niwqg_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->lane_stream[1]) cudaStreamSynchronize(h->lane_stream[1]);
     if (h->p2p)
         for (int r = 0; r < h->nranks; ++r)
@@ -812,6 +819,9 @@ static int create_impl(niwqg_handle* h) {
     DA(h->rscratch, B * h->npts * sizeof(double));
     h->lane_stream[0] = h->stream;
     h->lane_comm[0] = h->comm;
+    // measured: 7% at 512^2, nothing at 2048^2, slightly negative at 8192^2 (the step is a chain of dependent kernels,
+    // ~5 us each whatever launches them) -> small grids only
+    h->use_graphs = (h->nranks == 1) && N <= 1024 && !getenv("NIWQG_NO_GRAPH");
     if (h->nranks == 1 && !getenv("NIWQG_ONE_LANE")) {
         CK(cudaStreamCreateWithFlags(&h->lane_stream[1], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -1073,8 +1083,29 @@ int niwqg_step(niwqg_handle* h, int nsteps) {
         return -1;
     }
     for (int s = 0; s < nsteps; ++s) {
+        if (h->use_graphs && !h->prof && h->direct_steps >= 2) {
+            niwqg_handle::StepGraph& g = h->graphs[h->cq * 4 + h->cp * 2 + h->cc];
+            if (!g.exec) {
+                // capture one step issued from this buffer parity (host-side bookkeeping runs, kernels are recorded)
+                const long long l0 = h->launches;
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                int r = h->qg ? step_qg(h) : step_family(h);
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+                CK(ce);
+                CK(cudaGraphInstantiate(&g.exec, graph, 0));
+                CK(cudaGraphDestroy(graph));
+                g.cq = h->cq; g.cp = h->cp; g.cc = h->cc; g.launches = h->launches - l0;
+            } else {
+                h->cq = g.cq; h->cp = g.cp; h->cc = g.cc; h->launches += g.launches;
+            }
+            CK(cudaGraphLaunch(g.exec, h->stream));
+            continue;
+        }
         int r = h->qg ? step_qg(h) : step_family(h);
         if (r) return r;
+        h->direct_steps++;
     }
     return 0;
 }
