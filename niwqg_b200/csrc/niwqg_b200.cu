@@ -326,6 +326,28 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     h->launches += 2;
     return 0;
 }
+// One pass of an inverse transform in the natural single-GPU layout (shared row pass of phi / phiy, below).
+static int inv_row_pass(niwqg_handle* h, const cd* in, cd* out, int pro, int lane) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->N;
+    a.conj_in = 1; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+    a.deint_out = (h->deintC > 1);
+    { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, h->B, h->lane_stream[lane])); }
+    h->launches++;
+    return 0;
+}
+static int inv_col_pass(niwqg_handle* h, const cd* in, cd* out, int pro, int lane) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    const double sc = 1.0 / ((double)h->N * (double)h->N);
+    a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_col; a.nlines = h->N;
+    a.conj_in = 0; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
+    { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, h->B, h->lane_stream[lane])); }
+    h->launches++;
+    return 0;
+}
+
 #define FFT(...)                          \
     do {                                  \
         int r__ = fft2(h, __VA_ARGS__);   \
@@ -430,6 +452,28 @@ static BudgetArgs budget_args(niwqg_handle* h, int stage) {
 // phi-derived physical fields from the current phih: phi, lapphi (+lap2phi) always; phix, phiy when `grad`
 static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
     const cd* ph = h->phih[h->cp];
+    if (h->nranks == 1 && want_phi && grad && !lap) {
+        // phi = ifft(phih), phix = ifft(ik phih), phiy = ifft(il phih) in 2 row passes + 3 column passes instead of 3 + 3:
+        // the i l factor depends on the column-pass direction only, so phiy shares the row pass of phi and gets its
+        // factor (conjugated: the intermediate is in the conjugated domain) in the prologue of its column pass.
+        const bool par = h->lanes && !h->prof;
+        const int l1 = par ? 1 : 0;
+        if (par) {
+            CK(cudaEventRecord(h->ev_fork, h->lane_stream[0]));
+            CK(cudaStreamWaitEvent(h->lane_stream[1], h->ev_fork, 0));
+        }
+        int r = inv_row_pass(h, ph, h->phi, PRO_NONE, 0);
+        if (!r) r = inv_row_pass(h, ph, h->phix, PRO_IK, l1);
+        if (!r) r = inv_col_pass(h, h->phix, h->phix, PRO_NONE, l1);
+        if (!r) r = inv_col_pass(h, h->phi, h->phiy, PRO_IL_CONJ, 0);     // reads the shared row pass ...
+        if (!r) r = inv_col_pass(h, h->phi, h->phi, PRO_NONE, 0);         // ... before it is transformed in place
+        if (r) return r;
+        if (par) {
+            CK(cudaEventRecord(h->ev_join, h->lane_stream[1]));
+            CK(cudaStreamWaitEvent(h->lane_stream[0], h->ev_join, 0));
+        }
+        return 0;
+    }
     FftJob jobs[5];
     int n = 0;
     if (want_phi) jobs[n++] = FftJob{ph, h->phi, true, PRO_NONE};
