@@ -45,6 +45,7 @@ enum {
     PRO_NEG_WV2,   // * -(k^2+l^2)   (lapphi, Kernel.py:685)
     PRO_WV4,       // * (k^2+l^2)^2  (lap2phi, Kernel.py:688)
     PRO_UV,        // * (-il' + i*ik') with Nyquist lines zeroed: packs u + i v of a Hermitian ph (Kernel.py:681)
+    PRO_IK_CONJ,   // * conj(i k) = -i k (slab layout: the row pass is the second pass of an inverse transform)
     PRO_IL_CONJ,   // * conj(i l) = -i l: the i l factor applied in the SECOND pass of an inverse transform, whose
                    //   intermediate data lives in the conjugated domain (ifft = conj fft conj)
 };
@@ -104,6 +105,7 @@ __device__ __forceinline__ cd fft_prologue_one(const FftArgs& a, int row, int co
     if (PRO == PRO_IK) return make_double2(-k * x.y, k * x.x);
     if (PRO == PRO_IL) return make_double2(-l * x.y, l * x.x);
     if (PRO == PRO_IL_CONJ) return make_double2(l * x.y, -l * x.x);
+    if (PRO == PRO_IK_CONJ) return make_double2(k * x.y, -k * x.x);
     if (PRO == PRO_NEG_WV2) { const double w = -(k * k + l * l); return make_double2(w * x.x, w * x.y); }
     if (PRO == PRO_WV4) { double w = k * k + l * l; w = w * w; return make_double2(w * x.x, w * x.y); }
     if (PRO == PRO_UV) {
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
             NIWQG_PRO_CASE(PRO_WV4)
             NIWQG_PRO_CASE(PRO_UV)
             NIWQG_PRO_CASE(PRO_IL_CONJ)
+            NIWQG_PRO_CASE(PRO_IK_CONJ)
             default: break;
         }
     }
@@ -465,6 +468,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
             NIWQG_PRO_CASE(PRO_WV4)
             NIWQG_PRO_CASE(PRO_UV)
             NIWQG_PRO_CASE(PRO_IL_CONJ)
+            NIWQG_PRO_CASE(PRO_IK_CONJ)
             default: break;
         }
     }

@@ -348,6 +348,40 @@ static int inv_col_pass(niwqg_handle* h, const cd* in, cd* out, int pro, int lan
     return 0;
 }
 
+// The two halves of an inverse slab transform with the fused exchange, for transforms that share their first half
+// (wave_fields): column pass pushing into the peers' receive buffer `b` of `lane` + barrier, and the row pass that
+// reads a receive buffer.
+static int slab_inv_push(niwqg_handle* h, const cd* in, int pro, int lane, int* bout) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    cudaStream_t st = h->lane_stream[lane];
+    const int b = h->ybuf[lane];
+    h->ybuf[lane] ^= 1;
+    *bout = b;
+    a.push = 1;
+    for (int r = 0; r < h->nranks; ++r) a.peer[r] = h->peerY[lane][b][r];
+    int sh = 0;
+    while ((1 << sh) < h->nyl) ++sh;
+    a.nyl_shift = sh;
+    a.in = in; a.out = nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0; a.conj_out = 0;
+    a.tw = h->tw_col; a.nlines = h->ncl; a.conj_in = 1;
+    { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, 1, st)); }
+    { PROF_ON(PK_COMM, lane); NK(g_nccl.AllReduce(h->bar[lane], h->bar[lane], 1, ncclDouble, ncclSum, h->lane_comm[lane], st)); }
+    h->launches += 2;
+    return 0;
+}
+static int slab_inv_row(niwqg_handle* h, int lane, int b, cd* out, int pro) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    const double sc = 1.0 / ((double)h->N * (double)h->N);
+    a.in = h->Yp[lane][b]; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.conj_in = 0;
+    a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
+    a.deint_out = (h->deintC > 1);
+    { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, 1, h->lane_stream[lane])); }
+    h->launches++;
+    return 0;
+}
+
 #define FFT(...)                          \
     do {                                  \
         int r__ = fft2(h, __VA_ARGS__);   \
@@ -467,6 +501,28 @@ static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
         if (!r) r = inv_col_pass(h, h->phix, h->phix, PRO_NONE, l1);
         if (!r) r = inv_col_pass(h, h->phi, h->phiy, PRO_IL_CONJ, 0);     // reads the shared row pass ...
         if (!r) r = inv_col_pass(h, h->phi, h->phi, PRO_NONE, 0);         // ... before it is transformed in place
+        if (r) return r;
+        if (par) {
+            CK(cudaEventRecord(h->ev_join, h->lane_stream[1]));
+            CK(cudaStreamWaitEvent(h->lane_stream[0], h->ev_join, 0));
+        }
+        return 0;
+    }
+    if (h->nranks > 1 && h->p2p && h->exchange == 0 && want_phi && grad && !lap) {
+        // slab: the column pass comes first, so phi and phix share it (one exchange less): phix gets its conj(i k) in the
+        // prologue of its row pass, phiy = ifft(il phih) has its own column pass
+        const bool par = h->lanes && !h->prof;
+        const int l1 = par ? 1 : 0;
+        if (par) {
+            CK(cudaEventRecord(h->ev_fork, h->lane_stream[0]));
+            CK(cudaStreamWaitEvent(h->lane_stream[1], h->ev_fork, 0));
+        }
+        int b0 = 0, b1 = 0;
+        int r = slab_inv_push(h, ph, PRO_NONE, 0, &b0);
+        if (!r) r = slab_inv_push(h, ph, PRO_IL, l1, &b1);
+        if (!r) r = slab_inv_row(h, l1, b1, h->phiy, PRO_NONE);
+        if (!r) r = slab_inv_row(h, 0, b0, h->phi, PRO_NONE);
+        if (!r) r = slab_inv_row(h, 0, b0, h->phix, PRO_IK_CONJ);
         if (r) return r;
         if (par) {
             CK(cudaEventRecord(h->ev_join, h->lane_stream[1]));
