@@ -32,6 +32,7 @@
 // (niwqg/Kernel.py:565-566).
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda.h>      // CUtensorMap (TMA descriptors); the encoder is fetched through cudaGetDriverEntryPoint
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -73,6 +74,8 @@ struct FftArgs {
     int nyl_shift;    // log2(rows per rank)
     cd* peer[8];      // receive buffer of every rank (peer[rank] = own), CUDA-IPC mapped
     size_t mstride;   // elements between ensemble members
+    int tma_in;       // column pass, natural layout, one tile per line group: the tile is fetched by TMA (cp.async.bulk.tensor)
+                      // straight into shared memory instead of 16 B per-thread loads of half-used 128 B lines
     int one_cta_per_sm;   // request enough shared memory that only ONE CTA of this launch fits on an SM: leaves the other
                       // half of every SM to the pass that runs concurrently on the other lane (slab overlap)
     int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel;
@@ -236,6 +239,13 @@ __device__ __forceinline__ void st_async_cd(unsigned remote_addr, cd x, unsigned
                  ::"r"(remote_addr), "d"(x.x), "d"(x.y), "r"(remote_bar) : "memory");
 }
 
+// ---- TMA: 2-D tiled bulk tensor load global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(unsigned dst_smem, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_smem), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
 // L2 prefetch of the tile that the CTA `pf_groups` line groups ahead will load: the DRAM latency of that tile
 // is paid while the tiles in between are transformed, so a CTA's own loads are (mostly) L2 hits.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -261,10 +271,11 @@ __device__ __forceinline__ void fft_prefetch(const FftArgs& a, int group, int c,
 }
 
 template <int M, int W, int C, bool COL, bool NAT>
-__global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pass(FftArgs a) {
+__global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB)
+k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
     using TL = Tile<M, W, C, COL>;
     constexpr int N = TL::N;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* smem = reinterpret_cast<cd*>(smem_raw);
     const int tid = threadIdx.x;
     int w, j;
@@ -278,27 +289,53 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     cd* smtw = smem + (size_t)W * TL::LINE;
     cd v[fftc::E];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
-    // all 16 loads are issued back to back (nothing between them depends on loaded data); the prologue multiply and
-    // the conjugation of an inverse transform run afterwards, behind ONE uniform branch
-    if (a.pro == PRO_REAL_IN) {
-        const double* in = (const double*)a.in + mbase;
+    bool tma_done = false;
+    if constexpr (COL && NAT && C == 1 && M >= 256) {
+        if (a.tma_in) {
+            // the whole W x M tile by TMA: boxes of 256 rows x (W*16) bytes land densely ([row][W]) in the exchange buffer
+            const unsigned bar = smem_u32(smtw + TL::TWLEN);
+            if (tid == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(bar, (unsigned)(W * M * sizeof(cd)));
 #pragma unroll
-        for (int e = 0; e < fftc::E; ++e) {
-            const int m_ = j + e * TL::TPF;
-            const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
-            v[e] = make_double2(in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)], 0.0);
-        }
-    } else {
-        const cd* in = (const cd*)a.in + mbase;
+                for (int b4 = 0; b4 < M / 256; ++b4)
+                    tma_load_2d(smem_u32(smem + (size_t)b4 * 256 * W), &tmap, group * W * 2, (int)blockIdx.y * N + b4 * 256, bar);
+            }
+            for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+            mbar_wait(bar, 0);
 #pragma unroll
-        for (int e = 0; e < fftc::E; ++e) {
-            const int m_ = j + e * TL::TPF;
-            const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
-            v[e] = in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)];
+            for (int e = 0; e < fftc::E; ++e) v[e] = smem[(size_t)(j + e * TL::TPF) * W + w];
+            __syncthreads();        // the landing area is the exchange buffer of the stages
+            tma_done = true;
         }
     }
-    // stage twiddles -> shared memory, AFTER the data loads are out (this store waits for its own global load)
-    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+    if (!tma_done) {
+// all 16 loads are issued back to back (nothing between them depends on loaded data); the prologue multiply and
+        // the conjugation of an inverse transform run afterwards, behind ONE uniform branch
+        if (a.pro == PRO_REAL_IN) {
+            const double* in = (const double*)a.in + mbase;
+#pragma unroll
+            for (int e = 0; e < fftc::E; ++e) {
+                const int m_ = j + e * TL::TPF;
+                const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
+                v[e] = make_double2(in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)], 0.0);
+            }
+        } else {
+            const cd* in = (const cd*)a.in + mbase;
+#pragma unroll
+            for (int e = 0; e < fftc::E; ++e) {
+                const int m_ = j + e * TL::TPF;
+                const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
+                v[e] = in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)];
+            }
+        }
+        // stage twiddles -> shared memory, AFTER the data loads are out (this store waits for its own global load)
+        for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+    }
 #define NIWQG_PRO_CASE(P)                                                                     \
     case P:                                                                                   \
         _Pragma("unroll") for (int e = 0; e < fftc::E; ++e) {                                 \
@@ -387,7 +424,7 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     using TL = Tile<M, W, C, COL>;
     constexpr int N = TL::N;
     static_assert(C > 1 && C <= 8, "cluster sizes 2, 4, 8");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* smem = reinterpret_cast<cd*>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
@@ -515,6 +552,17 @@ __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB) k_fft_pa
     fft_stages<M, W, C, COL, NAT, true, 1>(v, j, w, c, smem, smtw, a, line, mbase);
 }
 
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled tma_encoder() {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return (PFN_tmapEncodeTiled)f;
+}
+
 // ---- pass geometry: (M, W, C) per grid size
 #ifndef NIWQG_COL_M
 #define NIWQG_COL_M 1024      // local transform length of a column pass
@@ -573,7 +621,26 @@ static cudaError_t launch_pass_g(const FftArgs& a, int batch, cudaStream_t st) {
             return cudaLaunchKernelEx(&cfg, k_fft_pass_dif<M, W, C, COL, NAT, true>, b);
         }
     }
-    return cudaLaunchKernelEx(&cfg, k_fft_pass<M, W, C, COL, NAT>, b);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    b.tma_in = 0;
+    if constexpr (COL && NAT && C == 1 && M >= 256 && W * sizeof(cd) < 128) {   // full 128 B rows (W = 8) are as fast with LDG
+        if (a.tma_in && a.pro != PRO_REAL_IN) {
+            // 2-D view of the input: inner dimension = one grid row as doubles, outer = all rows of all members
+            static PFN_tmapEncodeTiled enc = tma_encoder();
+            if (enc) {
+                const cuuint64_t dims[2] = {(cuuint64_t)2 * N, (cuuint64_t)N * batch};
+                const cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(cd)};
+                const cuuint32_t box[2] = {2 * W, 256};
+                const cuuint32_t estr[2] = {1, 1};
+                if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(a.in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    b.tma_in = 1;
+            }
+        }
+    }
+    return cudaLaunchKernelEx(&cfg, k_fft_pass<M, W, C, COL, NAT>, b, tmap);
 }
 
 template <int N, bool COL>

@@ -98,6 +98,8 @@ struct niwqg_handle {
                                 // the copy engines move the chunks to the peers (no SM involved, overlaps the other lane)
     cd* Xl[NLANE] = {nullptr, nullptr};   // per-lane send staging of the copy-engine exchange
     ncclComm_t comm = nullptr;
+    int tma = 1;                // column passes whose rows are narrower than a 128 B line fetch their tile by TMA
+                                // (1024^2: 4345 -> 4983 GB/s); NIWQG_TMA=0 switches it off
     int fft_variant = 6;        // FftArgs::variant: column clusters push (DIF, plain remote stores), row clusters pull (DIT):
                                 // measured best (profiles/r01b_cluster_variants.txt, r01d_async_push.txt)
     int pf_ctas = 296;          // L2 prefetch distance of the FFT passes in CTAs (~ one resident wave: 148 SMs x 2)
@@ -223,6 +225,7 @@ static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.xmap_in = a.xmap_out = 0;
     a.deint_in = a.deint_out = 0;
     a.one_cta_per_sm = 0;
+    a.tma_in = h->tma;
     a.xchunk = h->nyl * h->ncl;
     a.mstride = h->npts;
     a.pitch = h->ncl;
@@ -820,6 +823,7 @@ static int create_impl(niwqg_handle* h) {
     CK(cudaSetDevice(p.device));
     if (const char* e = getenv("NIWQG_PF_CTAS")) h->pf_ctas = atoi(e);   // tuning knob (0 = no prefetch)
     if (const char* e = getenv("NIWQG_FFT_VARIANT")) h->fft_variant = atoi(e);
+    if (const char* e = getenv("NIWQG_TMA")) h->tma = atoi(e);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
