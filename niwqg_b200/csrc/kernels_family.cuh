@@ -362,8 +362,9 @@ struct StageArgs {
     Grid g;
     int stage;        // 1..4
     int flags;
-    int do_q;         // 0 for YBJ (and for the phi half of a QL stage)
-    int do_phi;       // 0 for the q half of a QL stage
+    int do_q;         // 0 for YBJ (and for the phi half of a split stage)
+    int do_phi;       // 0 for the q half of a split stage
+    int sums_here;    // this launch evaluates the stage's spectral budget sums (exactly one launch per stage does)
     const cd *P1, *P2;
     const cd *y0q, *y0p;      // state at the start of the step
     cd *yq, *yp;              // current stage state (stage 1: output buffers distinct from y0)
@@ -392,11 +393,15 @@ __device__ __forceinline__ cd etd_update(int stage, cd y0, cd y1, cd Fn, cd& F0,
     return make_double2(r.x * fl, r.y * fl);
 }
 
+// ST (stage 1..4), DQ / DP (update the q / phi equation) are compile-time so that every instantiation carries only
+// the loads of its stage and equation: the fused (DQ && DP) body needs 128 registers and runs at ~79 % of the HBM
+// peak, the two halves launched back to back are lighter and faster (they share only the 8 B filter value).
+template <int ST, bool DQ, bool DP>
 __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
     const int N = a.g.N, H = N >> 1, NC = a.g.ncl;
     const size_t npts = (size_t)N * NC, mb = (size_t)blockIdx.y * npts;
     const size_t total = (size_t)(H + 1) * NC;
-    const int st = a.stage;
+    constexpr int st = ST;
     double s[SE_COUNT];
 #pragma unroll
     for (int k = 0; k < SE_COUNT; ++k) s[k] = 0.0;
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
         const bool self = (t1 == t2);
         const double fl1 = a.filtr[t1], fl2 = a.filtr[t2];
         const bool specb = (a.flags & MF_SPEC_BUDGET) != 0;
-        if (a.do_q && (specb || (a.flags & MF_HAS_LAP2))) {   // |phih|^2 moments on the pre-update phih (Kernel.py:629-652)
+        if (a.sums_here && (specb || (a.flags & MF_HAS_LAP2))) {   // |phih|^2 moments on the pre-update phih (Kernel.py:629-652)
             const cd c1 = (st == 1) ? a.y0p[i1] : a.yp[i1], c2 = (st == 1) ? a.y0p[i2] : a.yp[i2];
             const double k1 = a.g.dk * (double)sidx(kx, N), l1 = a.g.dk * (double)sidx(ky, N);
             const double wv2 = k1 * k1 + l1 * l1, w4 = wv2 * wv2;
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
             }
         }
         // ---------------- phi equation
-        if (a.do_phi) {
+        if constexpr (DP) {
             cd F1 = a.P2[i1], F2 = a.P2[i2];
             if ((a.flags & MF_FIX00) && mode00) {
                 const double* sd = a.sumsD + (size_t)blockIdx.y * SD_COUNT;
@@ -453,9 +458,8 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
                 if (st == 2 || st == 3) a.Fabp[i2] = Fabb;
             }
         }
-        if (!a.do_q) continue;
         // ---------------- q equation
-        {
+        if constexpr (DQ) {
             const double k1 = a.g.dk * (double)sidx(kx, N), l1 = a.g.dk * (double)sidx(ky, N);
             const double k2 = a.g.dk * (double)sidx(kxp, N), l2 = a.g.dk * (double)sidx(kyp, N);
             const cd p1 = a.P1[i1], p2 = a.P1[i2];
@@ -483,7 +487,18 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
             }
         }
     }
-    if (a.do_q) block_reduce_store<SE_COUNT>(s, a.partials);
+    if (a.sums_here) block_reduce_store<SE_COUNT>(s, a.partials);
+}
+
+template <bool DQ, bool DP>
+static cudaError_t launch_spec_stage(const StageArgs& a, dim3 grid, cudaStream_t st) {
+    switch (a.stage) {
+        case 1: k_spec_stage<1, DQ, DP><<<grid, NIWQG_PW_THREADS, 0, st>>>(a); break;
+        case 2: k_spec_stage<2, DQ, DP><<<grid, NIWQG_PW_THREADS, 0, st>>>(a); break;
+        case 3: k_spec_stage<3, DQ, DP><<<grid, NIWQG_PW_THREADS, 0, st>>>(a); break;
+        default: k_spec_stage<4, DQ, DP><<<grid, NIWQG_PW_THREADS, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
 }
 
 // ======================================================================

@@ -98,6 +98,7 @@ struct niwqg_handle {
                                 // the copy engines move the chunks to the peers (no SM involved, overlaps the other lane)
     cd* Xl[NLANE] = {nullptr, nullptr};   // per-lane send staging of the copy-engine exchange
     ncclComm_t comm = nullptr;
+    int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
     int tma = 1;                // column passes whose rows are narrower than a 128 B line fetch their tile by TMA
                                 // (1024^2: 4345 -> 4983 GB/s); NIWQG_TMA=0 switches it off
     int fft_variant = 6;        // FftArgs::variant: column clusters push (DIF, plain remote stores), row clusters pull (DIT):
@@ -627,9 +628,22 @@ static int step_family(niwqg_handle* h) {
             } else {
                 FFT(h->P2, h->P2, false, PRO_NONE, h->B);
             }
-            { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
-            CK(cudaGetLastError());
-            h->launches++;
+            if (ybj) {
+                sa.sums_here = 0;
+                { PROF(PK_SPEC); CK((launch_spec_stage<false, true>(sa, pw_grid(h), h->stream))); }
+                h->launches++;
+            } else if (h->split_stage) {
+                // two lighter kernels: q equation, then phi equation + the stage's spectral budget sums
+                sa.do_q = 1; sa.do_phi = 0; sa.sums_here = 0;
+                { PROF(PK_SPEC); CK((launch_spec_stage<true, false>(sa, pw_grid(h), h->stream))); }
+                sa.do_q = 0; sa.do_phi = 1; sa.sums_here = 1;
+                { PROF(PK_SPEC); CK((launch_spec_stage<false, true>(sa, pw_grid(h), h->stream))); }
+                h->launches += 2;
+            } else {
+                sa.sums_here = 1;
+                { PROF(PK_SPEC); CK((launch_spec_stage<true, true>(sa, pw_grid(h), h->stream))); }
+                h->launches++;
+            }
             if (st == 1) { h->cq = nq; h->cp = np; }
         } else {
             // repaired QL: jacobian_psi_phi reads qh AFTER the stage's q update (Kernel.py:326-332 order),
@@ -639,9 +653,8 @@ static int step_family(niwqg_handle* h) {
             CK(cudaGetLastError());
             FIN(SD_COUNT, h->sumsD);
             FFT(h->P1, h->P1, false, PRO_NONE, h->B);
-            sa.do_phi = 0;
-            { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
-            CK(cudaGetLastError());
+            sa.do_phi = 0; sa.sums_here = 1;
+            { PROF(PK_SPEC); CK((launch_spec_stage<true, false>(sa, pw_grid(h), h->stream))); }
             if (st == 1) h->cq = nq;
             int r = ql_wave_velocity(h);
             if (r) return r;
@@ -649,9 +662,8 @@ static int step_family(niwqg_handle* h) {
             { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
             CK(cudaGetLastError());
             FFT(h->P2, h->P2, false, PRO_NONE, h->B);
-            sa.do_q = 0; sa.do_phi = 1;
-            { PROF(PK_SPEC); k_spec_stage<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(sa); }
-            CK(cudaGetLastError());
+            sa.do_q = 0; sa.do_phi = 1; sa.sums_here = 0;
+            { PROF(PK_SPEC); CK((launch_spec_stage<false, true>(sa, pw_grid(h), h->stream))); }
             h->launches += 4;
             if (st == 1) h->cp = np;
         }
@@ -824,6 +836,7 @@ static int create_impl(niwqg_handle* h) {
     if (const char* e = getenv("NIWQG_PF_CTAS")) h->pf_ctas = atoi(e);   // tuning knob (0 = no prefetch)
     if (const char* e = getenv("NIWQG_FFT_VARIANT")) h->fft_variant = atoi(e);
     if (const char* e = getenv("NIWQG_TMA")) h->tma = atoi(e);
+    if (const char* e = getenv("NIWQG_SPLIT_STAGE")) h->split_stage = atoi(e);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
