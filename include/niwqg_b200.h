@@ -119,7 +119,9 @@ int niwqg_diagnostics(niwqg_handle* h, double* out);
  * pe_niw (refreshes phix/phiy), cfl. */
 int niwqg_status(niwqg_handle* h, double* out);
 /* Ke, Pw, Kw and the last stage's conversion terms: out[batch][NIWQG_S_COUNT] (only the
- * first 8 slots are defined). */
+ * first 8 slots are defined).  Coupled/UnCoupled evaluate the stage budgets in spectral space, where only the sums
+ * enter: slot GAMMA1 then holds gamma1+gamma2 and XI1 holds xi1+xi2 (GAMMA2 = XI2 = 0); niwqg_diagnostics returns
+ * the separate terms. */
 int niwqg_get_scalars(niwqg_handle* h, double* out);
 
 /* attribute read (Seam 3): copies one member's field to dst

@@ -1547,7 +1547,7 @@ int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t by
 
 int niwqg_fft2(niwqg_handle* h, const void* in, void* out, int kind) {
     CK(cudaSetDevice(h->p.device));
-    const size_t c = h->npts * sizeof(cd), r = h->npts * sizeof(double);
+    const size_t c = h->npts * sizeof(cd);
     const int N = h->N, nh = N / 2 + 1;
     if (h->nranks > 1 && (kind == NIWQG_FFT_R2C || kind == NIWQG_FFT_C2R)) { h->err = "fft2: half-spectrum kinds are single-GPU only"; return -1; }
     switch (kind) {
