@@ -151,6 +151,8 @@ int niwqg_nccl_unique_id(char* out128);
  * Without these calls the NCCL all-to-all path is used. */
 int niwqg_ipc_export(niwqg_handle* h, char* out, size_t bytes);
 int niwqg_ipc_import(niwqg_handle* h, const char* all_ranks, size_t bytes_per_rank);
+/* switch back to the NCCL all-to-all exchange (all ranks must agree, e.g. after one of them failed to import) */
+int niwqg_ipc_disable(niwqg_handle* h);
 
 int niwqg_sync(niwqg_handle* h);
 /* CUDA-event timing on the handle's stream: elapsed ms of `nsteps` steps */

@@ -39,7 +39,7 @@ EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
            "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id",
-           "niwqg_ipc_export", "niwqg_ipc_import"]
+           "niwqg_ipc_export", "niwqg_ipc_import", "niwqg_ipc_disable"]
 
 
 class Params(C.Structure):
@@ -88,6 +88,7 @@ def load():
     lib.niwqg_nccl_unique_id.argtypes = [vp]
     lib.niwqg_ipc_export.argtypes = [vp, vp, C.c_size_t]
     lib.niwqg_ipc_import.argtypes = [vp, vp, C.c_size_t]
+    lib.niwqg_ipc_disable.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -201,6 +202,9 @@ class Handle(object):
         if len(all_ranks_bytes) != self.IPC_BYTES * self.nranks:
             raise ValueError("expected %d bytes of IPC handles" % (self.IPC_BYTES * self.nranks))
         self._ck(self.lib.niwqg_ipc_import(self.h, all_ranks_bytes, self.IPC_BYTES))
+
+    def ipc_disable(self):
+        self._ck(self.lib.niwqg_ipc_disable(self.h))
 
     # -- seeding -----------------------------------------------------------
     def _host(self, a, dtype):

@@ -1047,6 +1047,13 @@ int niwqg_ipc_import(niwqg_handle* h, const char* all, size_t bytes_per_rank) {
     return 0;
 }
 
+int niwqg_ipc_disable(niwqg_handle* h) {   // back to the NCCL all-to-all exchange (e.g. when a peer could not map the buffers)
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->p2p = false;
+    return 0;
+}
+
 int niwqg_sync(niwqg_handle* h) {
     CK(cudaStreamSynchronize(h->stream));
     return 0;

@@ -61,10 +61,25 @@ def enable_peer_exchange(model, dist):
     import torch
     backend = dist.get_backend()
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    mine = torch.tensor(list(model._h.ipc_export()), dtype=torch.uint8, device=dev)
+    ok = 1
+    try:
+        mine = torch.tensor(list(model._h.ipc_export()), dtype=torch.uint8, device=dev)
+    except RuntimeError:
+        ok, mine = 0, torch.zeros(nat.Handle.IPC_BYTES, dtype=torch.uint8, device=dev)
     parts = [torch.empty_like(mine) for _ in range(model.nranks)]
     dist.all_gather(parts, mine)
-    model._h.ipc_import(b"".join(bytes(p.cpu().tolist()) for p in parts))
+    if ok:
+        try:
+            model._h.ipc_import(b"".join(bytes(p.cpu().tolist()) for p in parts))
+        except RuntimeError:
+            ok = 0
+    # every rank must use the same exchange: if anybody could not map its peers, all fall back to NCCL all-to-all
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        import logging
+        logging.getLogger(__name__).warning("CUDA IPC peer mapping unavailable: slab transposes use NCCL all-to-all")
+        model._h.ipc_disable()
     dist.barrier()
 
 
