@@ -54,3 +54,28 @@ def test_product_path_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+\S*oracle", src, re.M), "%s imports the oracle" % f
                 assert "niwqg_oracle" not in src, "%s references the oracle module" % f
+
+
+def test_initial_conditions_match_reference_golden():
+    """niwqg_b200.InitialConditions (host numpy, vectorised) reproduces the reference generators bit for bit:
+    LambDipole against the q0 the unmodified reference produced (tests/golden/make_golden.py), the plane-wave /
+    wave-packet formulas against their definitions (niwqg/InitialConditions.py:117-169)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    from cases import lamb_params, load_golden
+    from niwqg_b200 import InitialConditions as ic
+
+    class Grid(object):
+        pass
+    for nx, name in ((64, "coupled_lamb64_filt"), (128, "coupled_lamb128_nofilt_100")):
+        kw, U0, k0 = lamb_params(nx, True, 2, 10)
+        m = Grid()
+        m.nx = nx
+        m.x, m.y = np.meshgrid(np.arange(0.5, nx, 1.) / nx * kw["L"], np.arange(0.5, nx, 1.) / nx * kw["L"])
+        assert np.array_equal(ic.LambDipole(m, U=U0, R=2 * np.pi / k0), load_golden(name)["q0"])
+    k, l = 3e-5, 1e-5
+    assert np.array_equal(ic.PlaneWave(m, k=k, l=l, phase=0.3), np.exp(1j * (k * m.x + l * m.y) + 0.3))
+    wp = ic.WavePacket(m, k=k, l=l, R=1e5, x0=2e5, y0=1e5)
+    r = np.sqrt((m.x - 2e5) ** 2 + (m.y - 1e5) ** 2)
+    assert np.allclose(wp, np.exp(1j * (k * (m.x - 2e5) + l * (m.y - 1e5))) * np.exp(-(r / 1e5) ** 2), rtol=1e-15, atol=0)
