@@ -68,8 +68,8 @@ def test_initial_conditions_match_reference_golden():
 
     class Grid(object):
         pass
-    for nx, name in ((64, "coupled_lamb64_filt"), (128, "coupled_lamb128_nofilt_100")):
-        kw, U0, k0 = lamb_params(nx, True, 2, 10)
+    for nx, name, qg in ((64, "coupled_lamb64_filt", False), (64, "qg_lamb64_filt", True)):
+        kw, U0, k0 = lamb_params(nx, True, 2, 10, qg=qg)
         m = Grid()
         m.nx = nx
         m.x, m.y = np.meshgrid(np.arange(0.5, nx, 1.) / nx * kw["L"], np.arange(0.5, nx, 1.) / nx * kw["L"])
