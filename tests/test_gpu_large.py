@@ -96,3 +96,21 @@ def test_8192_step_conserves_and_budgets_close():
     m2.set_q(q); m2.set_phi(phi)
     m2._step_forward(); m2._step_forward()
     assert np.array_equal(q1, m2.q)
+
+
+@pytest.mark.parametrize("N", [2048, 4096, 8192])
+def test_cluster_transforms_are_bitwise_repeatable(N):
+    """The cluster kernels exchange through distributed shared memory behind barriers; a missing barrier would show up
+    as run-to-run differences (compute-sanitizer's racecheck is not available on the GPU pool).  Same input, several
+    back-to-back transforms (so different CTA placements and timings), bit-identical outputs, forward and inverse."""
+    from niwqg_b200 import _native as nat
+    h = nat.Handle(model=nat.MODEL_YBJ, nx=N, batch=1, device=0, L=5e5, dt=1e4, f=1e-4, N=0.01, m=0.025, nu=20., nuw=50.)
+    rng = np.random.RandomState(11)
+    x = rng.randn(N, N) + 1j * rng.randn(N, N)
+    X0 = h.fft2(x, nat.FFT_C2C_FWD)
+    x0 = h.fft2(X0, nat.FFT_C2C_INV)
+    for _ in range(3):
+        assert np.array_equal(h.fft2(x, nat.FFT_C2C_FWD), X0)
+        assert np.array_equal(h.fft2(X0, nat.FFT_C2C_INV), x0)
+    assert rel_l2(x0, x) < 5e-15
+    h.close()
