@@ -165,7 +165,7 @@ __device__ __forceinline__ void fft_emit(const FftArgs& a, size_t mbase, int lin
     if constexpr (C == 1) {
         fft_store<TL::N, COL, NAT>(a, mbase, line, k, x);
     } else if constexpr (DIF) {
-        const int n = (!NAT && a.deint_out) ? c * M + k : C * k + c;    // decimation in frequency: CTA c produced the outputs
+        const int n = a.deint_out ? c * M + k : C * k + c;    // decimation in frequency: CTA c produced the outputs
                                                                // congruent to c mod C (stored as one contiguous block
                                                                // when the physical side is de-interleaved)
         fft_store<TL::N, COL, NAT>(a, mbase, line, n, x);
@@ -321,7 +321,7 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
             for (int e = 0; e < fftc::E; ++e) {
                 const int m_ = j + e * TL::TPF;
-                const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
+                const int n = (C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;   // decimated sub-sequence of CTA c
                 v[e] = make_double2(in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)], 0.0);
             }
         } else {
@@ -329,7 +329,7 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
             for (int e = 0; e < fftc::E; ++e) {
                 const int m_ = j + e * TL::TPF;
-                const int n = (!NAT && C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
+                const int n = (C > 1 && a.deint_in) ? c * M + m_ : C * m_ + c;
                 v[e] = in[fft_index<N, COL, NAT>(a, a.xmap_in, line, n)];
             }
         }
@@ -646,7 +646,7 @@ static cudaError_t launch_pass_g(const FftArgs& a, int batch, cudaStream_t st) {
 template <int N, bool COL>
 static cudaError_t launch_pass_n(const FftArgs& a, int batch, cudaStream_t st) {
     // natural single-GPU geometry gets the kernels with compile-time strides
-    const bool nat = a.pitch == N && !a.push && !a.xmap_in && !a.xmap_out && !a.deint_in && !a.deint_out && !a.g.sym &&
+    const bool nat = a.pitch == N && !a.push && !a.xmap_in && !a.xmap_out && !a.g.sym &&
                      a.mstride == (size_t)N * N;
     return nat ? launch_pass_g<N, COL, true>(a, batch, st) : launch_pass_g<N, COL, false>(a, batch, st);
 }
