@@ -563,6 +563,92 @@ static PFN_tmapEncodeTiled tma_encoder() {
     return (PFN_tmapEncodeTiled)f;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Three-pass column transform for the longest lines (natural layout): the radix-R butterfly across the R row blocks of
+// M = N/R rows is a pure streaming pass (no shared memory, 1 KB-coalesced, out of place into a scratch array), and the
+// R x (N/W) remaining M-point transforms fit one tile each (full 128 B rows, no cluster, no DSMEM).  One more trip
+// through HBM than the cluster kernel, but both passes run at the one-tile rate.
+template <int N, int R>
+__global__ void __launch_bounds__(256) k_col_radix(FftArgs a) {
+    constexpr int M = N / R;
+    const int col = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
+    const size_t mbase = (size_t)blockIdx.z * a.mstride;
+    const cd* in = (const cd*)a.in + mbase;
+    cd* out = (cd*)a.out + mbase;
+    cd v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in[(size_t)(m + M * r) * N + col];
+    const cd w1 = a.twc[m];                                  // w_N^m
+#define NIWQG_PRO_CASE(P)                                                                     \
+    case P:                                                                                   \
+        _Pragma("unroll") for (int r = 0; r < R; ++r) v[r] = fft_prologue_one<N, P>(a, m + M * r, col, v[r]); \
+        break;
+    if (a.pro > PRO_REAL_IN) {
+        switch (a.pro) {
+            NIWQG_PRO_CASE(PRO_IK)
+            NIWQG_PRO_CASE(PRO_IL)
+            NIWQG_PRO_CASE(PRO_NEG_WV2)
+            NIWQG_PRO_CASE(PRO_WV4)
+            NIWQG_PRO_CASE(PRO_UV)
+            NIWQG_PRO_CASE(PRO_IL_CONJ)
+            default: break;
+        }
+    }
+#undef NIWQG_PRO_CASE
+    if (a.conj_in) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r].y = -v[r].y;
+    }
+    fftc::dft<R, 1>(v);
+    cd u[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) u[fftc::outidx<R>(p)] = v[p];
+    fftc::apply_twiddles<R, 1>(u, w1);                       // Y_q[m] *= w_N^{m q}
+#pragma unroll
+    for (int q = 0; q < R; ++q) out[(size_t)(m + M * q) * N + col] = u[q];
+}
+
+// second half: CTA (group, q) transforms the M rows [q M, (q+1) M) of its W columns and stores X[R k + q]
+template <int M, int W, int R>
+__global__ void __launch_bounds__(W * M / 16, 2) k_fft_colsub(FftArgs a) {
+    using TL = Tile<M, W, R, true>;
+    constexpr int N = TL::N;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cd* smem = reinterpret_cast<cd*>(smem_raw);
+    cd* smtw = smem + (size_t)W * TL::LINE;
+    const int tid = threadIdx.x, w = tid % W, j = tid / W;
+    const int q = (int)(blockIdx.x % R), group = (int)(blockIdx.x / R);
+    const int line = group * W + w;
+    const size_t mbase = (size_t)blockIdx.y * a.mstride;
+    const cd* in = (const cd*)a.in + mbase;
+    cd v[fftc::E];
+#pragma unroll
+    for (int e = 0; e < fftc::E; ++e) v[e] = in[(size_t)(q * M + j + e * TL::TPF) * N + line];
+    for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+    fft_stages<M, W, R, true, true, true, 1>(v, j, w, q, smem, smtw, a, line, mbase);
+}
+
+template <int N, int R, int W>
+static cudaError_t launch_col3(const FftArgs& a, void* scratch, int batch, cudaStream_t st) {
+    constexpr int M = N / R;
+    using TL = Tile<M, W, R, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_fft_colsub<M, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    FftArgs b = a;               // pass A: prologue + conj on load, no epilogue
+    b.out = scratch; b.epi = EPI_NONE; b.scale = 1.0; b.scale_im = 1.0;
+    k_col_radix<N, R><<<dim3(N / 256, M, batch), 256, 0, st>>>(b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    FftArgs c = a;               // pass B: plain transform + the pass's epilogue
+    c.in = scratch; c.pro = PRO_NONE; c.conj_in = 0;
+    k_fft_colsub<M, W, R><<<dim3((N / W) * R, batch), TL::T, TL::SMEM, st>>>(c);
+    return cudaGetLastError();
+}
+
 // ---- pass geometry: (M, W, C) per grid size
 #ifndef NIWQG_COL_M
 #define NIWQG_COL_M 1024      // local transform length of a column pass

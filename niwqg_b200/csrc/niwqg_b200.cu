@@ -98,6 +98,10 @@ struct niwqg_handle {
                                 // the copy engines move the chunks to the peers (no SM involved, overlaps the other lane)
     cd* Xl[NLANE] = {nullptr, nullptr};   // per-lane send staging of the copy-engine exchange
     ncclComm_t comm = nullptr;
+    int col3 = 1;               // 8192^2, one GPU: three-pass column transform (0.714 vs 0.771 ms for the cluster kernel);
+                                // NIWQG_COL3=0 switches back
+    cd* S3[2] = {nullptr, nullptr};   // its scratch array, one per lane
+    cd* tw_c3 = nullptr;              // stage twiddles of its 512-point local transforms
     int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
     int tma = 1;                // column passes whose rows are narrower than a 128 B line fetch their tile by TMA
                                 // (1024^2: 4345 -> 4983 GB/s); NIWQG_TMA=0 switches it off
@@ -217,6 +221,8 @@ static int slab_all_to_all(niwqg_handle* h, const cd* send, cd* recv) {
     return 0;
 }
 
+static cudaError_t launch_col_natural(niwqg_handle* h, const FftArgs& a, int batch, int lane);
+
 static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.twc = h->twc;
     a.dk = h->dk;
@@ -253,7 +259,7 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         a.in = out; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.tw = h->tw_col; a.nlines = h->N;
         a.conj_in = 0; a.conj_out = inverse ? 1 : 0;
         a.scale = sc; a.scale_im = inverse ? -sc : sc;
-        { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, batch, h->lane_stream[lane])); }
+        { PROF_ON(PK_FFT_COL, lane); CK(launch_col_natural(h, a, batch, lane)); }
         h->launches += 2;
         return 0;
     }
@@ -330,6 +336,18 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     h->launches += 2;
     return 0;
 }
+// column pass of the natural layout: the cluster kernel, or - 8192^2 with NIWQG_COL3 - the three-pass variant
+static cudaError_t launch_col_natural(niwqg_handle* h, const FftArgs& a, int batch, int lane) {
+    if (h->col3 && h->N == 8192 && batch == 1 && a.epi == EPI_NONE)
+    {
+        FftArgs b = a;
+        b.tw = h->tw_c3;
+        h->launches++;      // two kernels for this pass (the caller counts one)
+        return launch_col3<8192, 16, 8>(b, h->S3[lane], batch, h->lane_stream[lane]);
+    }
+    return launch_pass<true>(h->N, a, batch, h->lane_stream[lane]);
+}
+
 // One pass of an inverse transform in the natural single-GPU layout (shared row pass of phi / phiy, below).
 static int inv_row_pass(niwqg_handle* h, const cd* in, cd* out, int pro, int lane) {
     FftArgs a{};
@@ -347,7 +365,7 @@ static int inv_col_pass(niwqg_handle* h, const cd* in, cd* out, int pro, int lan
     const double sc = 1.0 / ((double)h->N * (double)h->N);
     a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_col; a.nlines = h->N;
     a.conj_in = 0; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
-    { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, h->B, h->lane_stream[lane])); }
+    { PROF_ON(PK_FFT_COL, lane); CK(launch_col_natural(h, a, h->B, lane)); }
     h->launches++;
     return 0;
 }
@@ -837,6 +855,7 @@ static int create_impl(niwqg_handle* h) {
     if (const char* e = getenv("NIWQG_FFT_VARIANT")) h->fft_variant = atoi(e);
     if (const char* e = getenv("NIWQG_TMA")) h->tma = atoi(e);
     if (const char* e = getenv("NIWQG_SPLIT_STAGE")) h->split_stage = atoi(e);
+    if (const char* e = getenv("NIWQG_COL3")) h->col3 = atoi(e);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -939,6 +958,16 @@ static int create_impl(niwqg_handle* h) {
     // measured: 7% at 512^2, nothing at 2048^2, slightly negative at 8192^2 (the step is a chain of dependent kernels,
     // ~5 us each whatever launches them) -> small grids only
     h->use_graphs = (h->nranks == 1) && N <= 1024 && !getenv("NIWQG_NO_GRAPH");
+    if (h->nranks == 1 && h->col3 && N == 8192 && B == 1) {
+        DA(h->S3[0], fsz); DA(h->S3[1], fsz);
+        std::vector<cd> tw3;
+        build_twiddles(512, tw3);
+        DA(h->tw_c3, tw3.size() * cb);
+        CK(cudaMemcpyAsync(h->tw_c3, tw3.data(), tw3.size() * cb, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        h->col3 = 0;
+    }
     if (h->nranks == 1 && !getenv("NIWQG_ONE_LANE")) {
         CK(cudaStreamCreateWithFlags(&h->lane_stream[1], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
