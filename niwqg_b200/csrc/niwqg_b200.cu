@@ -14,6 +14,7 @@
 #include <nccl.h>
 #include "../../include/niwqg_b200.h"
 #include "fft2d.cuh"
+#include "fft_split.cuh"
 #include "kernels_family.cuh"
 #include "kernels_qg.cuh"
 
@@ -102,6 +103,12 @@ struct niwqg_handle {
                                 // NIWQG_COL3=0 switches back
     cd* S3[2] = {nullptr, nullptr};   // its scratch array, one per lane
     cd* tw_c3 = nullptr;              // stage twiddles of its 512-point local transforms
+    // split transforms (fft_split.cuh): x = 2 x N/2 on de-interleaved physical rows, y = 16 x N/16, three streaming launches
+    // per 2-D transform.  Default for 8192^2 on one GPU (1.09 vs 1.22 ms per transform); NIWQG_SPLIT=1 forces it for every
+    // N >= 2048 (tests), NIWQG_SPLIT=0 switches it off.
+    int split = 0;
+    cd* T[3] = {nullptr, nullptr, nullptr};   // scratch arrays of the split path
+    cd *tw_half = nullptr, *tw_m = nullptr;   // stage twiddles of the N/2-point rows and of the N/16-point column transforms
     int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
     int tma = 1;                // column passes whose rows are narrower than a 128 B line fetch their tile by TMA
                                 // (1024^2: 4345 -> 4983 GB/s); NIWQG_TMA=0 switches it off
@@ -116,7 +123,7 @@ struct niwqg_handle {
     size_t prof_used = 0;
 };
 
-enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_COUNT };
+enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_FFT_P, PK_COUNT };
 
 static cudaEvent_t prof_event(niwqg_handle* h) {
     if (h->prof_used == h->prof_pool.size()) {
@@ -238,6 +245,72 @@ static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.pitch = h->ncl;
 }
 
+// ---- split path (fft_split.cuh): the three launches of a 2-D transform
+static int split_rows(niwqg_handle* h, const void* in, void* out, int pro, int epi, double sc, bool conj_out) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    const int Nh = h->N / 2;
+    a.in = in; a.out = out; a.pro = pro; a.epi = epi; a.tw = h->tw_half;
+    a.nlines = 2 * h->N; a.pitch = Nh; a.mstride = (size_t)Nh * Nh; a.g = Grid{Nh, h->dk, Nh, Nh / 2, 0, 0};
+    a.conj_in = 0; a.conj_out = conj_out ? 1 : 0; a.scale = sc; a.scale_im = conj_out ? -sc : sc;
+    { PROF(PK_FFT_ROW); CK(launch_pass<false>(Nh, a, 1, h->stream)); }
+    h->launches++;
+    return 0;
+}
+static int split_colsub(niwqg_handle* h, const cd* in, cd* out, bool dit) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    a.in = in; a.out = out; a.pro = PRO_NONE; a.epi = EPI_NONE; a.tw = h->tw_m; a.scale = 1.0; a.scale_im = 1.0;
+    cudaError_t e = cudaErrorInvalidValue;
+    {
+        PROF(PK_FFT_COL);
+        switch (h->N) {
+            case 2048: e = dit ? launch_split_colsub<2048, true>(a, h->stream) : launch_split_colsub<2048, false>(a, h->stream); break;
+            case 4096: e = dit ? launch_split_colsub<4096, true>(a, h->stream) : launch_split_colsub<4096, false>(a, h->stream); break;
+            case 8192: e = dit ? launch_split_colsub<8192, true>(a, h->stream) : launch_split_colsub<8192, false>(a, h->stream); break;
+        }
+    }
+    CK(e);
+    h->launches++;
+    return 0;
+}
+static int split_p(niwqg_handle* h, const cd* in, cd* const* out, const int* pro, int nout, bool dit, bool conj_in) {
+    SplitPArgs p{};
+    p.in = in; p.nout = nout; p.conj_in = conj_in ? 1 : 0; p.scale = 1.0; p.dk = h->dk; p.twc = h->twc;
+    for (int o = 0; o < nout; ++o) { p.out[o] = out[o]; p.pro[o] = pro[o]; }
+    cudaError_t e = cudaErrorInvalidValue;
+    {
+        PROF(PK_FFT_P);
+        switch (h->N) {
+            case 2048: e = dit ? launch_split_p<2048, true>(p, h->stream) : launch_split_p<2048, false>(p, h->stream); break;
+            case 4096: e = dit ? launch_split_p<4096, true>(p, h->stream) : launch_split_p<4096, false>(p, h->stream); break;
+            case 8192: e = dit ? launch_split_p<8192, true>(p, h->stream) : launch_split_p<8192, false>(p, h->stream); break;
+        }
+    }
+    CK(e);
+    h->launches++;
+    return 0;
+}
+// forward: rows (in -> out), M-point column transforms (out -> T0), radix-16 x radix-2 combine (T0 -> out)
+// inverse: prologue + conj + radix stage (in -> T0), M-point column transforms (T0 -> out), rows in place with conj + 1/N^2
+static int fft2_split(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro, int epi, void* real_out) {
+    int r;
+    if (!inverse) {
+        if ((r = split_rows(h, in, out, pro == PRO_REAL_IN ? PRO_REAL_IN : PRO_NONE, EPI_NONE, 1.0, false))) return r;
+        if ((r = split_colsub(h, out, h->T[0], true))) return r;
+        cd* outs[1] = {out};
+        const int pros[1] = {PRO_NONE};
+        if ((r = split_p(h, h->T[0], outs, pros, 1, true, false))) return r;
+        return 0;
+    }
+    cd* outs[1] = {h->T[0]};
+    const int pros[1] = {pro};
+    if ((r = split_p(h, (const cd*)in, outs, pros, 1, false, true))) return r;
+    if ((r = split_colsub(h, h->T[0], out, false))) return r;
+    const double sc = 1.0 / ((double)h->N * (double)h->N);
+    return split_rows(h, out, epi == EPI_REAL_OUT ? real_out : (void*)out, PRO_NONE, epi, sc, true);
+}
+
 // 2-D c2c transform of `batch` members: in -> out (may alias), forward or inverse.
 // One GPU: row pass then column pass.  Slab: forward = row pass (rows are local) -> all-to-all -> column pass
 // (columns are local); inverse = column pass -> all-to-all -> row pass.  The spectral prologue multiply and the
@@ -248,6 +321,7 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
     fft_common_args(h, a);
     const double sc = inverse ? 1.0 / ((double)h->N * (double)h->N) : 1.0;
     void* final_out = (epi == EPI_REAL_OUT) ? real_out : (void*)out;
+    if (h->split && batch == 1) return fft2_split(h, in, out, inverse, pro, epi, real_out);
     if (h->nranks == 1) {
         // pass 1: rows
         a.in = in; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.tw = h->tw_row; a.nlines = h->N;
@@ -415,7 +489,7 @@ static int slab_inv_row(niwqg_handle* h, int lane, int b, cd* out, int pro) {
 struct FftJob { const void* in; cd* out; bool inverse; int pro; };
 static int fft2_group(niwqg_handle* h, const FftJob* jobs, int n) {
     // (one GPU: the column pass of one transform, bound by the DSMEM exchange, runs next to the row pass of the other)
-    const bool par = h->lanes && (h->p2p || h->nranks == 1) && !h->prof && n > 1;
+    const bool par = h->lanes && (h->p2p || h->nranks == 1) && !h->prof && n > 1 && !h->split;
     if (!par) {
         for (int i = 0; i < n; ++i) FFT(jobs[i].in, jobs[i].out, jobs[i].inverse, jobs[i].pro, h->B);
         return 0;
@@ -508,7 +582,19 @@ static BudgetArgs budget_args(niwqg_handle* h, int stage) {
 // phi-derived physical fields from the current phih: phi, lapphi (+lap2phi) always; phix, phiy when `grad`
 static int wave_fields(niwqg_handle* h, bool want_phi, bool grad, bool lap) {
     const cd* ph = h->phih[h->cp];
-    if (h->nranks == 1 && want_phi && grad && !lap) {
+    if (h->split && want_phi && grad && !lap) {
+        // phi, phix, phiy: the streaming radix stage reads phih once and writes the three intermediates
+        const int pros[3] = {PRO_NONE, PRO_IK, PRO_IL};
+        cd* dst[3] = {h->phi, h->phix, h->phiy};
+        int r = split_p(h, ph, h->T, pros, 3, false, true);
+        const double sc = 1.0 / ((double)h->N * (double)h->N);
+        for (int o = 0; o < 3 && !r; ++o) {
+            r = split_colsub(h, h->T[o], dst[o], false);
+            if (!r) r = split_rows(h, dst[o], dst[o], PRO_NONE, EPI_NONE, sc, true);
+        }
+        return r;
+    }
+    if (h->nranks == 1 && !h->split && want_phi && grad && !lap) {
         // phi = ifft(phih), phix = ifft(ik phih), phiy = ifft(il phih) in 2 row passes + 3 column passes instead of 3 + 3:
         // the i l factor depends on the column-pass direction only, so phiy shares the row pass of phi and gets its
         // factor (conjugated: the intermediate is in the conjugated domain) in the prologue of its column pass.
@@ -869,6 +955,11 @@ static int create_impl(niwqg_handle* h) {
     // de-interleaved physical x order (row pass = push kernel with contiguous stores): correct, but measured slower
     // than the pull kernel on the natural layout (0.578 vs 0.535 ms per 8192^2 row pass), so it is opt-in
     if (N > NIWQG_ROW_MAXM && getenv("NIWQG_DEINT")) { h->deintM = NIWQG_ROW_MAXM; h->deintC = N / NIWQG_ROW_MAXM; }
+    if (h->nranks == 1 && h->B == 1 && !h->qg && N >= 2048) {
+        const char* e = getenv("NIWQG_SPLIT");
+        h->split = e ? (atoi(e) != 0) : (N == 8192);
+        if (h->split) { h->deintM = N / 2; h->deintC = 2; }
+    }
     h->g = Grid{N, 2.0 * M_PI / p.L, h->ncl, h->ncl / 2, h->rank, h->nranks > 1 ? 1 : 0};
     if (h->nranks > 1) {
         int r = nccl_load(h->err);
@@ -958,6 +1049,19 @@ static int create_impl(niwqg_handle* h) {
     // measured: 7% at 512^2, nothing at 2048^2, slightly negative at 8192^2 (the step is a chain of dependent kernels,
     // ~5 us each whatever launches them) -> small grids only
     h->use_graphs = (h->nranks == 1) && N <= 1024 && !getenv("NIWQG_NO_GRAPH");
+    if (h->split) {
+        for (int o = 0; o < 3; ++o) DA(h->T[o], fsz);
+        std::vector<cd> tw;
+        build_twiddles(N / 2, tw);
+        DA(h->tw_half, tw.size() * cb);
+        CK(cudaMemcpyAsync(h->tw_half, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        build_twiddles(N / 16, tw);
+        DA(h->tw_m, tw.size() * cb);
+        CK(cudaMemcpyAsync(h->tw_m, tw.data(), tw.size() * cb, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->col3 = 0;
+    }
     if (h->nranks == 1 && h->col3 && N == 8192 && B == 1) {
         DA(h->S3[0], fsz); DA(h->S3[1], fsz);
         std::vector<cd> tw3;
