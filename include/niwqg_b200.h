@@ -29,6 +29,7 @@ extern "C" {
 /* constructor keywords of niwqg/Kernel.py:70-98 and niwqg/QGModel.py:65-91 that
  * reach the arithmetic */
 typedef struct niwqg_params {
+    size_t struct_size; /* = sizeof(niwqg_params): a binding built against another layout is rejected, not over-read */
     int model;          /* NIWQG_MODEL_*                                        */
     int nx;             /* grid edge, power of two, 32..8192 (ny==nx, F9)        */
     int batch;          /* ensemble members sharing these parameters (>=1)       */

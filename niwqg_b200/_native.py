@@ -43,7 +43,8 @@ EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "
 
 
 class Params(C.Structure):
-    _fields_ = [("model", C.c_int), ("nx", C.c_int), ("batch", C.c_int), ("device", C.c_int),
+    _fields_ = [("struct_size", C.c_size_t),
+                ("model", C.c_int), ("nx", C.c_int), ("batch", C.c_int), ("device", C.c_int),
                 ("L", C.c_double), ("dt", C.c_double), ("U", C.c_double), ("f", C.c_double), ("N", C.c_double),
                 ("m", C.c_double), ("nu", C.c_double), ("nu4", C.c_double), ("mu", C.c_double),
                 ("nuw", C.c_double), ("nu4w", C.c_double), ("muw", C.c_double), ("beta", C.c_double),
@@ -155,6 +156,7 @@ class Handle(object):
             os.environ["NIWQG_NCCL_LIB"] = path
         self.lib = load()
         p = Params()
+        p.struct_size = C.sizeof(Params)
         for k, v in kw.items():
             if k == "nccl_id":      # raw 128 bytes (a c_char array would stop at the first NUL)
                 if v is None or len(v) != 128:

@@ -336,14 +336,22 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_phys_rhs(PhysArgs a) {
     if (!nosums) block_reduce_store<SD_COUNT>(s, a.partials);
 }
 
-// sums over the blocks of one member in a fixed order: out[member][k]
-__global__ void k_finalize(const double* __restrict__ partials, int nblk, int K, double* __restrict__ out, int is_max) {
-    const int m = blockIdx.x, k = threadIdx.x;
-    if (k >= K) return;
+// sums over the blocks of one member in a fixed order: out[member][k].  256 threads: thread (part, k) adds the blocks
+// part, part + 16, ... of sum k, then thread k adds the 16 parts - always the same order, so results are reproducible.
+__global__ void __launch_bounds__(256) k_finalize(const double* __restrict__ partials, int nblk, int K, double* __restrict__ out, int is_max) {
+    __shared__ double sh[16][17];
+    const int m = blockIdx.x, k = threadIdx.x & 15, part = threadIdx.x >> 4;
     const double* p = partials + (size_t)m * nblk * K;
-    double x = is_max ? p[k] : 0.0;
-    for (int b = is_max ? 1 : 0; b < nblk; ++b) x = is_max ? fmax(x, p[(size_t)b * K + k]) : x + p[(size_t)b * K + k];
-    out[(size_t)m * K + k] = x;
+    double x = is_max ? -1.0e300 : 0.0;
+    if (k < K)
+        for (int b = part; b < nblk; b += 16) x = is_max ? fmax(x, p[(size_t)b * K + k]) : x + p[(size_t)b * K + k];
+    sh[part][k] = x;
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double y = sh[0][threadIdx.x];
+        for (int q = 1; q < 16; ++q) y = is_max ? fmax(y, sh[q][threadIdx.x]) : y + sh[q][threadIdx.x];
+        out[(size_t)m * K + threadIdx.x] = y;
+    }
 }
 
 // ======================================================================

@@ -16,6 +16,7 @@
 #include "fft2d.cuh"
 #include "fft_split.cuh"
 #include "kernels_family.cuh"
+#include "kernels_fused.cuh"
 #include "kernels_qg.cuh"
 
 static std::string g_create_error;
@@ -109,6 +110,9 @@ struct niwqg_handle {
     int split = 0;
     cd* T[3] = {nullptr, nullptr, nullptr};   // scratch arrays of the split path
     cd *tw_half = nullptr, *tw_m = nullptr;   // stage twiddles of the N/2-point rows and of the N/16-point column transforms
+    int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
+                                // NIWQG_FUSED=0 runs the stage as launches of its own
+    int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
     int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
     int tma = 1;                // column passes whose rows are narrower than a 128 B line fetch their tile by TMA
                                 // (1024^2: 4345 -> 4983 GB/s); NIWQG_TMA=0 switches it off
@@ -507,9 +511,9 @@ static int fft2_group(niwqg_handle* h, const FftJob* jobs, int n) {
     return 0;
 }
 
-static int finalize(niwqg_handle* h, int K, double* out, int is_max = 0) {
+static int finalize(niwqg_handle* h, int K, double* out, int is_max = 0, int nblk = NIWQG_PW_BLOCKS) {
     PROF(PK_SMALL);
-    k_finalize<<<h->B, 32, 0, h->stream>>>(h->part, NIWQG_PW_BLOCKS, K, out, is_max);
+    k_finalize<<<h->B, 256, 0, h->stream>>>(h->part, nblk, K, out, is_max);
     CK(cudaGetLastError());
     h->launches += 1;
     if (h->nranks > 1)   // every rank reduced its slab; the grid-wide sum / max is the same on all ranks afterwards
@@ -701,7 +705,89 @@ static int ql_wave_velocity(niwqg_handle* h) {   // uq, vq from the current qh (
     return 0;
 }
 
+// Coupled / UnCoupled step on the split transform path with the fused spectral kernels (kernels_fused.cuh): the
+// forward transforms stop after their M-point column transforms, the kernel that consumes the spectrum does the radix
+// combine itself; the kernels that produce a spectrum emit the radix stage of its inverse transforms.
+template <int N>
+static int step_family_fused_n(niwqg_handle* h) {
+    const int oq = h->cq, op = h->cp, nq = 1 - oq, np = 1 - op;
+    const bool wave = (h->flags & MF_WAVE_PV) != 0;
+    const double sc = 1.0 / ((double)N * (double)N);
+    const int grid = h->fused_grid;
+    int r;
+    for (int st = 1; st <= 4; ++st) {
+        PhysArgs pa = phys_args(h, 0);
+        { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
+        CK(cudaGetLastError());
+        h->launches++;
+        FIN(SD_COUNT, h->sumsD);
+        if ((r = split_rows(h, h->P1, h->P1, PRO_NONE, EPI_NONE, 1.0, false))) return r;
+        if ((r = split_colsub(h, h->P1, h->T[0], true))) return r;
+        if ((r = split_rows(h, h->P2, h->P2, PRO_NONE, EPI_NONE, 1.0, false))) return r;
+        if ((r = split_colsub(h, h->P2, h->T[1], true))) return r;
+        FStageArgs fa{};
+        StageArgs& sa = fa.s;
+        sa.g = h->g; sa.stage = st; sa.flags = h->flags; sa.do_q = 1; sa.do_phi = 1; sa.sums_here = 1;
+        sa.P1 = h->P1; sa.P2 = h->P2;
+        sa.y0q = h->qh[oq]; sa.y0p = h->phih[op]; sa.yq = h->qh[nq]; sa.yp = h->phih[np];
+        sa.y1q = h->y1q; sa.y1p = h->y1p; sa.F0q = h->F0q; sa.F0p = h->F0p; sa.Fabq = h->Fabq; sa.Fabp = h->Fabp;
+        sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
+        fa.twc = h->twc; fa.dk = h->dk;
+        fa.T = h->T[0];
+        { PROF(PK_SPEC); CK((launch_fstage<N>(fa, false, grid, h->stream))); }
+        fa.T = h->T[1];
+        fa.out[0] = h->T[1]; fa.out[1] = h->T[2]; fa.out[2] = h->T[0];   // in place over its own input; T0 is free again
+        fa.nout = wave ? 3 : 1;
+        { PROF(PK_SPEC); CK((launch_fstage<N>(fa, true, grid, h->stream))); }
+        h->launches += 2;
+        if (st == 1) { h->cq = nq; h->cp = np; }
+        FIN(SE_COUNT, h->sumsE, 0, grid);
+        { PROF(PK_SMALL); k_budget<<<h->B, 32, 0, h->stream>>>(budget_args(h, st)); }
+        CK(cudaGetLastError());
+        h->launches++;
+        // self.phi = ifft(phih); phix, phiy (jacobian_phic_phi): the remaining two launches of each inverse transform
+        if ((r = split_colsub(h, h->T[1], h->phi, false))) return r;
+        if ((r = split_rows(h, h->phi, h->phi, PRO_NONE, EPI_NONE, sc, true))) return r;
+        if (wave) {
+            if ((r = split_colsub(h, h->T[2], h->phix, false))) return r;
+            if ((r = split_rows(h, h->phix, h->phix, PRO_NONE, EPI_NONE, sc, true))) return r;
+            if ((r = split_colsub(h, h->T[0], h->phiy, false))) return r;
+            if ((r = split_rows(h, h->phiy, h->phiy, PRO_NONE, EPI_NONE, sc, true))) return r;
+            { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
+            CK(cudaGetLastError());
+            h->launches++;
+            if ((r = split_rows(h, h->W, h->W, PRO_NONE, EPI_NONE, 1.0, false))) return r;
+            if ((r = split_colsub(h, h->W, h->T[0], true))) return r;
+        }
+        // _invert(); _calc_rel_vorticity(); u, v
+        FInvertArgs ia{};
+        ia.i.g = h->g; ia.i.flags = h->flags; ia.i.f = h->p.f; ia.i.qh = h->qh[h->cq]; ia.i.filtr = h->filtr;
+        ia.i.ph = h->ph; ia.i.qs = h->qs; ia.i.W = h->T[0]; ia.i.qwh = (wave && st == 4) ? h->qwh : nullptr;
+        ia.i.inv_jscale = 1.0 / h->jscale; ia.i.partials = h->part;
+        ia.T = h->T[0]; ia.out_uv = h->T[1]; ia.out_qs = h->T[2]; ia.twc = h->twc; ia.dk = h->dk;
+        { PROF(PK_SPEC); CK((launch_finvert<N>(ia, wave, grid, h->stream))); }
+        h->launches++;
+        FIN(SI_COUNT, h->sumsI, 0, grid);
+        if ((r = split_colsub(h, h->T[1], h->uv, false))) return r;
+        if ((r = split_rows(h, h->uv, h->uv, PRO_NONE, EPI_NONE, sc, true))) return r;
+        if ((r = split_colsub(h, h->T[2], h->qs, false))) return r;
+        if ((r = split_rows(h, h->qs, h->qs, PRO_NONE, EPI_NONE, sc, true))) return r;
+    }
+    return 0;
+}
+static int step_family_fused(niwqg_handle* h) {
+    switch (h->N) {
+        case 2048: return step_family_fused_n<2048>(h);
+        case 4096: return step_family_fused_n<4096>(h);
+        case 8192: return step_family_fused_n<8192>(h);
+    }
+    h->err = "fused step: unsupported grid";
+    return -1;
+}
+
 static int step_family(niwqg_handle* h) {
+    if (h->split && h->fused && (h->flags & MF_SPEC_BUDGET) && !(h->flags & (MF_YBJ | MF_QL_ADV)))
+        return step_family_fused(h);
     const bool ybj = (h->flags & MF_YBJ) != 0, ql = (h->flags & MF_QL_ADV) != 0;
     const int oq = h->cq, op = h->cp;          // y0 buffers
     const int nq = ybj ? oq : 1 - oq, np = 1 - op;
@@ -958,6 +1044,7 @@ static int create_impl(niwqg_handle* h) {
     if (h->nranks == 1 && h->B == 1 && !h->qg && N >= 2048) {
         const char* e = getenv("NIWQG_SPLIT");
         h->split = e ? (atoi(e) != 0) : (N == 8192);
+        if (const char* f = getenv("NIWQG_FUSED")) h->fused = atoi(f);
         if (h->split) { h->deintM = N / 2; h->deintC = 2; }
     }
     h->g = Grid{N, 2.0 * M_PI / p.L, h->ncl, h->ncl / 2, h->rank, h->nranks > 1 ? 1 : 0};
@@ -1113,6 +1200,10 @@ static int create_impl(niwqg_handle* h) {
 int niwqg_create(const niwqg_params* p, niwqg_handle** out) {
     if (!p || !out) { g_create_error = "null argument"; return -1; }
     *out = nullptr;
+    if (p->struct_size != sizeof(niwqg_params)) {
+        g_create_error = "niwqg_params.struct_size does not match this library (binding built against another header)";
+        return -1;
+    }
     const int N = p->nx;
     if (N < 32 || N > 8192 || (N & (N - 1))) { g_create_error = "nx must be a power of two in [32, 8192]"; return -1; }
     if (p->batch < 1) { g_create_error = "batch must be >= 1"; return -1; }
@@ -1480,14 +1571,14 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
         CK(cudaMemcpyAsync(sq.data(), h->sumsD, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(sc.data(), h->scal, sc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        double gam[64] = {0};
+        std::vector<double> gam((size_t)B, 0.0);
         if (ps) {
             // Gamma_c = 2*mean(lapc * irfft2(jacobian_psi_c))  (QGModel.py:731)
             int r = qg_gamma_c(h);
             if (r) return r;
             CK(cudaMemcpyAsync(sg.data(), h->sumsD, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
-            for (int m = 0; m < B && m < 64; ++m) gam[m] = 2.0 * sg[m] / M2;
+            for (int m = 0; m < B; ++m) gam[m] = 2.0 * sg[m] / M2;
         }
         for (int m = 0; m < B; ++m) {
             double* o = out + (size_t)m * NIWQG_S_COUNT;
@@ -1501,7 +1592,7 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
             o[NIWQG_S_CHI_Q] = -h->p.nu4 * s[QS_CHIQ] / M2;
             if (ps) {
                 const double C2 = s[QS_C2] / M2, gradC2 = s[QS_GRADC2] / M2, lapc2 = s[QS_LAPC2] / M2, lap2clapc = s[QS_LAP2CLAPC] / M2;
-                o[NIWQG_S_C2] = C2; o[NIWQG_S_GRADC2] = gradC2; o[NIWQG_S_GAMMA_C] = m < 64 ? gam[m] : 0.0;
+                o[NIWQG_S_C2] = C2; o[NIWQG_S_GRADC2] = gradC2; o[NIWQG_S_GAMMA_C] = gam[m];
                 o[NIWQG_S_EP_C] = -2 * h->p.nu4c * lapc2 - 2 * h->p.nu * gradC2 - 2 * h->p.muc * C2;          // QGModel.py:595-598
                 o[NIWQG_S_CHI_C] = 2 * h->p.nu4c * lap2clapc - 2 * h->p.nu * lapc2 - 2 * h->p.muc * gradC2;  // QGModel.py:600-604
             }

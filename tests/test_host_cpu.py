@@ -79,3 +79,53 @@ def test_initial_conditions_match_reference_golden():
     wp = ic.WavePacket(m, k=k, l=l, R=1e5, x0=2e5, y0=1e5)
     r = np.sqrt((m.x - 2e5) ** 2 + (m.y - 1e5) ** 2)
     assert np.allclose(wp, np.exp(1j * (k * (m.x - 2e5) + l * (m.y - 1e5))) * np.exp(-(r / 1e5) ** 2), rtol=1e-15, atol=0)
+
+
+def _header_params_fields():
+    """(name, ctype-string, array-length) of every field of struct niwqg_params, in declaration order."""
+    header = open(os.path.join(ROOT, "include", "niwqg_b200.h")).read()
+    body = re.search(r"typedef struct niwqg_params \{(.*?)\} niwqg_params;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(size_t|int|double|char)\s+(.*)", decl)
+        assert m, decl
+        for name in m.group(2).split(","):
+            name = name.strip()
+            arr = re.match(r"(\w+)\[(\d+)\]", name)
+            fields.append((arr.group(1), m.group(1), int(arr.group(2))) if arr else (name, m.group(1), 0))
+    return fields
+
+
+def _ctypes_fields(cls):
+    import ctypes as C
+    names = {C.c_size_t: "size_t", C.c_int: "int", C.c_double: "double"}
+    out = []
+    for name, tp in cls._fields_:
+        if hasattr(tp, "_length_"):
+            out.append((name, "char", tp._length_))
+        else:
+            out.append((name, names[tp], 0))
+    return out
+
+
+def test_params_struct_matches_header_in_native_and_in_integration_doc():
+    """The ctypes mirror of niwqg_params (niwqg_b200/_native.py) and the binding INTEGRATION.md tells a reference maintainer
+    to add must list exactly the fields of include/niwqg_b200.h, in order - a shorter struct would be over-read by
+    niwqg_create (which now also checks struct_size)."""
+    import ctypes as C
+    want = _header_params_fields()
+    assert want[0] == ("struct_size", "size_t", 0) and want[-1] == ("nccl_id", "char", 128) and len(want) >= 27
+    from niwqg_b200 import _native
+    assert _ctypes_fields(_native.Params) == want
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    snippet = re.search(r"```python\n(import ctypes as C.*?)```", doc, re.S).group(1)
+    cls_src = snippet[snippet.index("class Params"):]
+    cls_src = cls_src[:re.search(r"\n\S", cls_src[1:]).start() + 1]       # up to the next top-level statement
+    ns = {"C": C}
+    exec(cls_src, ns)
+    assert _ctypes_fields(ns["Params"]) == want
+    assert C.sizeof(ns["Params"]) == C.sizeof(_native.Params)
