@@ -148,6 +148,22 @@ __device__ __forceinline__ void eq_load(EqIn& in, const cd* __restrict__ y0, con
     else { in.c0 = __ldg(&t.E[i]); in.c1 = __ldg(&t.f0[i]); in.c2 = __ldg(&t.fab[i]); in.c3 = __ldg(&t.fc[i]); }
     in.fl = __ldg(&filtr[i]);
 }
+// L2 prefetch of the same operands a few elements ahead: costs no registers, and turns the HBM latency of the register
+// loads into an L2 hit (at 512 threads per SM the two elements in flight per thread cannot cover HBM latency alone)
+template <int ST, bool PHI>
+__device__ __forceinline__ void eq_prefetch(const cd* y0, const cd* y, const cd* y1, const cd* F0, const cd* Fab, const TableSet& t,
+                                            const double* filtr, size_t i) {
+    prefetch_l2(&y0[i]);
+    if (PHI && ST >= 2) prefetch_l2(&y[i]);
+    if (ST >= 3) { prefetch_l2(&F0[i]); prefetch_l2(&Fab[i]); }
+    if (ST == 3) prefetch_l2(&y1[i]);
+    if (ST <= 3) { prefetch_l2(&t.E2[i]); prefetch_l2(&t.Q[i]); }
+    else { prefetch_l2(&t.E[i]); prefetch_l2(&t.f0[i]); prefetch_l2(&t.fab[i]); prefetch_l2(&t.fc[i]); }
+    if ((threadIdx.x & 1) == 0) prefetch_l2(&filtr[i]);
+}
+constexpr int FUSED_PD = 0;     // L2 prefetch distance in elements (0 = off: measured slower, 24.1 vs 22.2 ms of spectral kernels per step)
+// register pipeline depth of the element loop per stage: as deep as 128 registers allow
+template <int ST> struct FusedDepth { static constexpr int Q = ST <= 2 ? 4 : 3, PHI = ST <= 2 ? 4 : (ST == 3 ? 3 : 2), INV = 6; };
 // etd_update (kernels_family.cuh) on preloaded operands; F0 / Fab come back as what the stage stores
 template <int ST>
 __device__ __forceinline__ cd eq_update(const EqIn& in, cd y0, cd Fn, cd& F0, cd& Fab) {
@@ -187,13 +203,15 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
         __syncthreads();
         const double k1 = a.dk * (double)sidx(t.col, N);
         const size_t i0 = (size_t)t.fam * N + t.col;
-        EqIn in[2];
-        eq_load<ST, false>(in[0], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i0);
+        constexpr int D = FusedDepth<ST>::Q;
+        EqIn in[D];
+#pragma unroll
+        for (int p = 0; p < D - 1; ++p) eq_load<ST, false>(in[p], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i0 + (size_t)p * M * N);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int ky = t.fam + M * q;
             const size_t i1 = i0 + (size_t)q * M * N;
-            if (q + 1 < 16) eq_load<ST, false>(in[(q + 1) & 1], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i1 + (size_t)M * N);
+            if (q + D - 1 < 16) eq_load<ST, false>(in[(q + D - 1) % D], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i1 + (size_t)(D - 1) * M * N);
             const cd p1 = xs[q * 256 + tid], p2 = xs[fused_qp(t, q) * 256 + t.ptid];
             const double l1 = a.dk * (double)sidx(ky, N);
             // A = fft(u q)(K) = 0.5 (P(K) + conj P(-K)),  B = fft(v q)(K) = -0.5 i (P(K) - conj P(-K));  Fn = -(i k A + i l B)
@@ -201,7 +219,7 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
             const cd B = make_double2(0.5 * (p1.y + p2.y), -0.5 * (p1.x - p2.x));
             cd F1 = make_double2(k1 * A.y + l1 * B.y, -(k1 * A.x + l1 * B.x));
             if (ky == 0 && t.col == 0) F1 = make_double2(0.0, 0.0);
-            const EqIn& e = in[q & 1];
+            const EqIn& e = in[q % D];
             cd F0a, Faba;
             const cd n1 = eq_update<ST>(e, e.y0, F1, F0a, Faba);
             a.s.yq[i1] = n1;
@@ -238,14 +256,16 @@ __global__ void __launch_bounds__(256, 2) k_fstage_phi(FStageArgs a) {
         double s[SE_COUNT];
 #pragma unroll
         for (int k = 0; k < SE_COUNT; ++k) s[k] = 0.0;
-        EqIn in[2];
-        eq_load<ST, true>(in[0], a.s.y0p, a.s.yp, a.s.y1p, a.s.F0p, a.s.Fabp, a.s.tp, a.s.filtr, i0);
+        constexpr int D = FusedDepth<ST>::PHI;
+        EqIn in[D];
+#pragma unroll
+        for (int p = 0; p < D - 1; ++p) eq_load<ST, true>(in[p], a.s.y0p, a.s.yp, a.s.y1p, a.s.F0p, a.s.Fabp, a.s.tp, a.s.filtr, i0 + (size_t)p * M * N);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int ky = t.fam + M * q;
             const size_t i1 = i0 + (size_t)q * M * N;
-            if (q + 1 < 16) eq_load<ST, true>(in[(q + 1) & 1], a.s.y0p, a.s.yp, a.s.y1p, a.s.F0p, a.s.Fabp, a.s.tp, a.s.filtr, i1 + (size_t)M * N);
-            const EqIn& e = in[q & 1];
+            if (q + D - 1 < 16) eq_load<ST, true>(in[(q + D - 1) % D], a.s.y0p, a.s.yp, a.s.y1p, a.s.F0p, a.s.Fabp, a.s.tp, a.s.filtr, i1 + (size_t)(D - 1) * M * N);
+            const EqIn& e = in[q % D];
             cd F1 = xs[q * 256 + tid];
             const cd cur1 = (ST == 1) ? e.y0 : e.cur;
             if (specb || (a.s.flags & MF_HAS_LAP2)) {     // |phih|^2 moments on the pre-update phih (Kernel.py:629-652)
@@ -326,15 +346,16 @@ __global__ void __launch_bounds__(256, 2) k_finvert(FInvertArgs a) {
             in.q2 = __ldg(&a.i.qh[(size_t)kyp * N + colp]);
             if (HASW) in.fl = __ldg(&a.i.filtr[i0 + (size_t)q * M * N]);
         };
-        InvIn in[3];
-        load(in[0], 0);
-        load(in[1], 1);
+        constexpr int D = FusedDepth<1>::INV;
+        InvIn in[D];
+#pragma unroll
+        for (int p = 0; p < D - 1; ++p) load(in[p], p);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int ky = t.fam + M * q;
             const size_t i1 = i0 + (size_t)q * M * N;
-            if (q + 2 < 16) load(in[(q + 2) % 3], q + 2);
-            const InvIn& e = in[q % 3];
+            if (q + D - 1 < 16) load(in[(q + D - 1) % D], q + D - 1);
+            const InvIn& e = in[q % D];
             const double l1 = a.dk * (double)sidx(ky, N);
             const double wv2 = __dadd_rn(__dmul_rn(k1, k1), __dmul_rn(l1, l1));
             const double wv2i = (wv2 != 0.0) ? 1.0 / wv2 : 0.0;
