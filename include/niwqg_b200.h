@@ -107,6 +107,23 @@ int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device);
 /* set_c (niwqg/QGModel.py:522-534) */
 int niwqg_set_c(niwqg_handle* h, const double* c, int on_device);
 
+/* Initial conditions generated on the device (niwqg/InitialConditions.py), then seeded exactly like set_q / set_phi:
+ * no whole-grid host array is involved (at 8192^2 the reference generators need several 1 GiB arrays, a Python loop
+ * over every grid point and four host round trips of the FFT seam).
+ *   LAMB_DIPOLE (U, R)            q    InitialConditions.py:77-114
+ *   MCWILLIAMS  (k0, E, seed)     q    :4-41   random red spectrum; rand01 = the caller's np.random.rand(N, N) for
+ *   DANIOUX     (k0, E, seed)     q    :43-75  parity with the host generator, or NULL: Philox4x32-10(seed)
+ *   WAVEPACKET  (k, l, R, x0, y0) phi  :117-145
+ *   PLANEWAVE   (k, l, phase)     phi  :147-169 (the phase scales the amplitude, as in the reference)
+ *   UNIFORM     (re, im)          phi  uniform near-inertial wave, examples/LambDipole.py:52 */
+#define NIWQG_IC_LAMB_DIPOLE 0
+#define NIWQG_IC_MCWILLIAMS  1
+#define NIWQG_IC_DANIOUX     2
+#define NIWQG_IC_WAVEPACKET  3
+#define NIWQG_IC_PLANEWAVE   4
+#define NIWQG_IC_UNIFORM     5
+int niwqg_ic(niwqg_handle* h, int kind, const double* params, int nparams, const double* rand01);
+
 /* nsteps calls of _step_etdrk4 (niwqg/Kernel.py:307-397; YBJModel.py:52-87;
  * QGModel.py:328-407) back to back, asynchronous on the handle's stream. */
 int niwqg_step(niwqg_handle* h, int nsteps);

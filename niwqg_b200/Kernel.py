@@ -28,6 +28,9 @@ class _DeviceField(object):
 
 
 class _Scalar(object):
+    """Integrated budget kept on the device (Ke, Pw, Kw).  Read-only: the reference lets user code assign to it, which
+    here would silently shadow the device value, so an assignment raises instead."""
+
     def __init__(self, name):
         self.name = name
 
@@ -36,6 +39,32 @@ class _Scalar(object):
             return self
         v = obj._h.scalars()[:, nat.S[self.name]]
         return float(v[0]) if obj.batch == 1 else v
+
+    def __set__(self, obj, value):
+        raise AttributeError("%s lives on the device (set it through set_q / set_phi)" % self.name)
+
+
+class _LazyGrid(object):
+    """Whole-grid host array of the reference's grid set-up (niwqg/Kernel.py:232-265), built on first use and cached.
+    The device never reads these (wavenumbers are recomputed from indices in the kernels), and at 8192^2 the ten of them
+    are 6 GB of host memory and most of the model construction time."""
+
+    def __init__(self, name, build):
+        self.name, self.build = name, build
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        v = self.build(obj)
+        obj.__dict__[self.name] = v        # non-data descriptor: the instance attribute wins from now on
+        return v
+
+
+def _wv2i(self):
+    out = np.zeros_like(self.wv2)
+    nz = self.wv2 != 0.
+    out[nz] = self.wv2[nz] ** -1
+    return out
 
 
 class Kernel(object):
@@ -63,6 +92,17 @@ class Kernel(object):
     expchw = _DeviceField("EXPCHW"); expch_hw = _DeviceField("EXPCH_HW"); Qhw = _DeviceField("QHWCOEF")
     f0w = _DeviceField("F0W"); fabw = _DeviceField("FABW"); fcw = _DeviceField("FCW")
     Ke = _Scalar("KE"); Pw = _Scalar("PW"); Kw = _Scalar("KW")
+    # whole-grid host arrays, on demand
+    x = _LazyGrid("x", lambda s: np.meshgrid(np.arange(0.5, s.nx, 1.) / s.nx * s.L, np.arange(0.5, s.ny, 1.) / s.ny * s.W)[0])
+    y = _LazyGrid("y", lambda s: np.meshgrid(np.arange(0.5, s.nx, 1.) / s.nx * s.L, np.arange(0.5, s.ny, 1.) / s.ny * s.W)[1])
+    k = _LazyGrid("k", lambda s: np.meshgrid(s.kk, s.ll)[0])
+    l = _LazyGrid("l", lambda s: np.meshgrid(s.kk, s.ll)[1])
+    ik = _LazyGrid("ik", lambda s: 1j * s.k)
+    il = _LazyGrid("il", lambda s: 1j * s.l)
+    wv2 = _LazyGrid("wv2", lambda s: s.k ** 2 + s.l ** 2)
+    wv = _LazyGrid("wv", lambda s: np.sqrt(s.wv2))
+    wv4 = _LazyGrid("wv4", lambda s: s.wv2 ** 2)
+    wv2i = _LazyGrid("wv2i", _wv2i)
 
     def __init__(self, nx=128, ny=None, L=5e5, dt=10000., twrite=1000., tmax=250000., use_filter=True,
                  cflmax=0.8, U=.0, f=1.e-4, N=0.01, m=0.025, g=9.81, nu4=0, nu4w=0, nu=20, nuw=50., mu=0, muw=0,
@@ -97,6 +137,10 @@ class Kernel(object):
         self.device = device
         # slab decomposition of this grid over nranks GPUs, one process per GPU (niwqg_b200/slab.py builds these)
         self.rank, self.nranks, self._nccl_id = rank, nranks, nccl_id
+        if save_to_disk and nranks > 1:
+            # every rank would write its own rows under the same file names (niwqg/Saving.py has no notion of ranks)
+            raise NotImplementedError("save_to_disk with a slab-decomposed grid: gather with niwqg_b200.slab.gather_rows "
+                                      "and write from one rank")
 
         self._initialize_logger()
         self.logger.info(self.model)
@@ -129,27 +173,17 @@ class Kernel(object):
         self.tc = 0
 
     def _initialize_grid(self):
-        """Host copies of the small grid arrays users and helpers read (niwqg/Kernel.py:227-265)."""
-        self.x, self.y = np.meshgrid(np.arange(0.5, self.nx, 1.) / self.nx * self.L,
-                                     np.arange(0.5, self.ny, 1.) / self.ny * self.W)
+        """Scalars and 1-D arrays of niwqg/Kernel.py:227-265; the 2-D arrays (x, y, k, l, ik, il, wv2, wv, wv4, wv2i)
+        are lazy class attributes (_LazyGrid)."""
         self.dk = 2. * pi / self.L
         self.dl = 2. * pi / self.L
         self.nl = self.ny
         self.nk = self.nl
         self.ll = self.dl * np.append(np.arange(0., self.nx / 2), np.arange(-self.nx / 2, 0.))
         self.kk = self.ll.copy()
-        self.k, self.l = np.meshgrid(self.kk, self.ll)
-        self.ik = 1j * self.k
-        self.il = 1j * self.l
         self.dx = self.L / self.nx
         self.dy = self.W / self.ny
         self.M = self.nx * self.ny
-        self.wv2 = self.k ** 2 + self.l ** 2
-        self.wv = np.sqrt(self.wv2)
-        self.wv4 = self.wv2 ** 2
-        iwv2 = self.wv2 != 0.
-        self.wv2i = np.zeros_like(self.wv2)
-        self.wv2i[iwv2] = self.wv2[iwv2] ** -1
 
     def _initialize_logger(self):
         """niwqg/Kernel.py:286-304."""
@@ -265,6 +299,60 @@ class Kernel(object):
 
     def _calc_cfl(self):
         return self._status_value(3)
+
+    # -------------------------------- the reference's per-quantity helpers (user scripts call them directly)
+    def _invert(self):
+        """niwqg/Kernel.py:488-490 hook: the inversion runs on the device inside set_q and every stage; the carried
+        fields (ph, q, qw, u, v) are always consistent with qh, so there is nothing left to do here."""
+
+    def _calc_rel_vorticity(self):
+        """niwqg/Kernel.py:492-501 / CoupledModel.py:145-152: q_psi is carried on the device (attribute ``q_psi``)."""
+
+    def _diag_slot(self, name):
+        d = self._h.scalars("diagnostics")
+        v = d[:, nat.S[name]]
+        return float(v[0]) if self.batch == 1 else v
+
+    def _calc_energy_conversion(self):
+        """niwqg/Kernel.py:664-701: gamma1, gamma2, xi1, xi2, pi of the current state."""
+        self._calc_derived_fields()
+
+    def _calc_icke_niw(self):
+        """niwqg/Kernel.py:703-706."""
+        self._calc_derived_fields()
+
+    def _calc_conc(self):
+        return self._diag_slot("CONC")
+
+    def _calc_skewness(self):
+        return self._diag_slot("SKEW")
+
+    def _calc_ens(self):
+        return self._diag_slot("ENS")
+
+    def _calc_ep_phi(self):
+        return self._diag_slot("EP_PHI")
+
+    def _calc_ep_psi(self):
+        return self._diag_slot("EP_PSI")
+
+    def _calc_chi_q(self):
+        return self._diag_slot("CHI_Q")
+
+    def _calc_chi_phi(self):
+        return self._diag_slot("CHI_PHI")
+
+    def _calc_strain(self):
+        """niwqg/Kernel.py:503-509: geostrophic rate of strain from the device ph (three transforms on the CUDA engine)."""
+        ph = self.ph
+        pxx, pyy = self.ifft(-self.k * self.k * ph).real, self.ifft(-self.l * self.l * ph).real
+        pxy = self.ifft(-self.k * self.l * ph).real
+        self.qg_strain = 4 * (pxy ** 2) + (pxx - pyy) ** 2
+
+    def _calc_OW(self):
+        """niwqg/Kernel.py:511-518: Okubo-Weiss parameter."""
+        self._calc_strain()
+        return self.qg_strain ** 2 - self.q_psi ** 2
 
     # ------------------------------------------------------------ diagnostics
     def _calc_derived_fields(self):

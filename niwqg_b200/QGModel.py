@@ -6,7 +6,7 @@ import numpy as np
 from numpy import pi
 
 from . import _native as nat
-from .Kernel import _DeviceField, _Scalar
+from .Kernel import _DeviceField, _Scalar, _LazyGrid, _wv2i
 from .Diagnostics import add_diagnostic, increment_diagnostics
 from .Saving import initialize_save_snapshots, save_setup, save_snapshots, save_diagnostics
 
@@ -78,28 +78,29 @@ class Model(object):
         v = self._h.scalars()[:, nat.S["CVAR"]]
         return float(v[0]) if self.batch == 1 else v
 
+    # whole-grid host arrays of niwqg/QGModel.py:232-269, built on first use (the device recomputes wavenumbers itself)
+    x = _LazyGrid("x", lambda s: np.meshgrid(np.arange(0.5, s.nx, 1.) / s.nx * s.L, np.arange(0.5, s.ny, 1.) / s.ny * s.W)[0])
+    y = _LazyGrid("y", lambda s: np.meshgrid(np.arange(0.5, s.nx, 1.) / s.nx * s.L, np.arange(0.5, s.ny, 1.) / s.ny * s.W)[1])
+    k = _LazyGrid("k", lambda s: np.meshgrid(s.kk, s.ll)[0])
+    l = _LazyGrid("l", lambda s: np.meshgrid(s.kk, s.ll)[1])
+    ik = _LazyGrid("ik", lambda s: 1j * s.k)
+    il = _LazyGrid("il", lambda s: 1j * s.l)
+    wv2 = _LazyGrid("wv2", lambda s: s.k ** 2 + s.l ** 2)
+    wv = _LazyGrid("wv", lambda s: np.sqrt(s.wv2))
+    wv4 = _LazyGrid("wv4", lambda s: s.wv2 ** 2)
+    wv2i = _LazyGrid("wv2i", _wv2i)
+
     def _initialize_grid(self):
-        """niwqg/QGModel.py:232-269."""
-        self.x, self.y = np.meshgrid(np.arange(0.5, self.nx, 1.) / self.nx * self.L,
-                                     np.arange(0.5, self.ny, 1.) / self.ny * self.W)
+        """Scalars and 1-D arrays of niwqg/QGModel.py:232-269 (half spectrum: nk = nx/2 + 1)."""
         self.dk = 2. * pi / self.L
         self.dl = 2. * pi / self.L
         self.nl = self.ny
         self.nk = self.nx // 2 + 1
         self.ll = self.dl * np.append(np.arange(0., self.nx / 2), np.arange(-self.nx / 2, 0.))
         self.kk = self.dk * np.arange(0., self.nk)
-        self.k, self.l = np.meshgrid(self.kk, self.ll)
-        self.ik = 1j * self.k
-        self.il = 1j * self.l
         self.dx = self.L / self.nx
         self.dy = self.W / self.ny
         self.M = self.nx * self.ny
-        self.wv2 = self.k ** 2 + self.l ** 2
-        self.wv = np.sqrt(self.wv2)
-        self.wv4 = self.wv2 ** 2
-        iwv2 = self.wv2 != 0.
-        self.wv2i = np.zeros_like(self.wv2)
-        self.wv2i[iwv2] = self.wv2[iwv2] ** -1
 
     def _initialize_logger(self):
         self.logger = logging.getLogger(__name__)

@@ -58,8 +58,10 @@ def save_snapshots(self, fields=['t', 'q', 'p']):
             for field in fields:
                 if field == 't':
                     h5file.create_dataset(field, data=(self.t))
-                elif hasattr(self, field):
-                    h5file.create_dataset(field, data=getattr(self, field))
+                    continue
+                val = getattr(self, field, None)       # ONE device-to-host copy per field (hasattr would be a second one)
+                if val is not None:
+                    h5file.create_dataset(field, data=val)
 
 
 def save_diagnostics(self):

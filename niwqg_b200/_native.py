@@ -38,7 +38,7 @@ JAC_PSI_Q, JAC_PHIC_PHI, JAC_PSI_PHI = range(3)
 EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "niwqg_set_phi", "niwqg_set_c",
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
-           "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id",
+           "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id", "niwqg_ic",
            "niwqg_ipc_export", "niwqg_ipc_import", "niwqg_ipc_disable"]
 
 
@@ -71,6 +71,7 @@ def load():
     lib.niwqg_last_error.restype = C.c_char_p
     for n in ("niwqg_set_q", "niwqg_set_phi", "niwqg_set_c"):
         getattr(lib, n).argtypes = [vp, vp, ip]
+    lib.niwqg_ic.argtypes = [vp, ip, vp, ip, vp]
     lib.niwqg_step.argtypes = [vp, ip]
     for n in ("niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars"):
         getattr(lib, n).argtypes = [vp, vp]
@@ -234,6 +235,19 @@ class Handle(object):
     def set_c(self, c):
         a = self._host(c, np.float64)
         self._ck(self.lib.niwqg_set_c(self.h, a.ctypes.data, 0))
+        self.sync()
+
+    IC_KINDS = {"LambDipole": 0, "McWilliams1984": 1, "Danioux2015": 2, "WavePacket": 3, "PlaneWave": 4, "Uniform": 5}
+
+    def ic(self, kind, params, rand01=None):
+        """Generate an initial condition on the device and seed the model with it (niwqg_ic)."""
+        prm = np.ascontiguousarray(params, dtype=np.float64)
+        r = None
+        if rand01 is not None:
+            r = np.ascontiguousarray(rand01, dtype=np.float64)
+            if r.size != self.N * self.N:
+                raise ValueError("rand01 must hold N*N uniform numbers")
+        self._ck(self.lib.niwqg_ic(self.h, self.IC_KINDS[kind], prm.ctypes.data, prm.size, r.ctypes.data if r is not None else None))
         self.sync()
 
     def set_q_device(self, ptr):

@@ -151,6 +151,8 @@ struct InvertArgs {
     int flags;
     double f;
     double inv_jscale;   // undoes k_phys_wavepv's scaling of the Jacobian partner
+    int filtr_sym;       // filtr(K) == filtr(-K) everywhere (the exponential filter; NOT the 2/3-rule mask, whose band
+                         // [N/3, 2N/3) holds index N/3 but not its mirror 2N/3): spares the second filter load
     const cd* W;      // forward transform of the [B] products (MF_WAVE_PV)
     const cd* qh;
     const double* filtr;
@@ -202,15 +204,22 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_invert(InvertArgs a) 
             continue;
         }
         const cd Hq = make_double2(0.5 * (q1.x + q2.x), 0.5 * (q1.y - q2.y));   // Herm(qh)(K)
-        cd qw = make_double2(0.0, 0.0);
+        cd qw = make_double2(0.0, 0.0), qwb = qw;
+        double fl1 = 0.0, fl2 = 0.0;
         if (a.flags & MF_WAVE_PV) {
             const cd W1 = a.W[i1], W2 = a.W[i2];
             const cd A = make_double2(0.5 * (W1.x + W2.x), 0.5 * (W1.y - W2.y));     // fft(|phi|^2)(K)
             cd Jc = make_double2(a.inv_jscale * 0.5 * (W1.y + W2.y), a.inv_jscale * -0.5 * (W1.x - W2.x));   // -0.5i (W1 - conj W2)
             if (ky == 0 && kx == 0) Jc = make_double2(0.0, 0.0);
-            const double fl = a.filtr[(size_t)ky * NC + lc];
-            qw.x = 0.5 * (0.5 * (-wv2 * A.x) + Jc.x) / a.f * fl;
-            qw.y = 0.5 * (0.5 * (-wv2 * A.y) + Jc.y) / a.f * fl;
+            // qwh = base * filtr per element (CoupledModel.py:86); what enters p and qw is Re ifft(...), i.e. the
+            // Hermitian part, whose coefficient is base * (filtr(K) + filtr(-K)) / 2
+            fl1 = a.filtr[(size_t)ky * NC + lc];
+            fl2 = a.filtr_sym ? fl1 : a.filtr[(size_t)kyp * NC + lcp];
+            const double fs = 0.5 * (fl1 + fl2);
+            qwb.x = 0.5 * (0.5 * (-wv2 * A.x) + Jc.x) / a.f;
+            qwb.y = 0.5 * (0.5 * (-wv2 * A.y) + Jc.y) / a.f;
+            qw.x = qwb.x * fs;
+            qw.y = qwb.y * fs;
         }
         const cd ph1 = make_double2(wv2i * qw.x - wv2i * Hq.x, wv2i * qw.y - wv2i * Hq.y);
         {   // Re(Hq conj ph(K)) + Re(conj(Hq) conj ph(-K)), ph(-K) = conj ph(K)
@@ -222,11 +231,11 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_invert(InvertArgs a) 
         // qs(K) = Hq + i qw ; qs(-K) = conj(Hq) + i conj(qw)
         a.ph[i1] = ph1;
         a.qs[i1] = make_double2(Hq.x - qw.y, Hq.y + qw.x);
-        if (a.qwh) a.qwh[i1] = qw;
+        if (a.qwh) a.qwh[i1] = make_double2(qwb.x * fl1, qwb.y * fl1);
         if (!self) {
             a.ph[i2] = make_double2(ph1.x, -ph1.y);
             a.qs[i2] = make_double2(Hq.x + qw.y, -Hq.y + qw.x);
-            if (a.qwh) a.qwh[i2] = make_double2(qw.x, -qw.y);
+            if (a.qwh) a.qwh[i2] = make_double2(qwb.x * fl2, -qwb.y * fl2);
         }
     }
     if (a.partials) block_reduce_store<SI_COUNT>(s, a.partials);

@@ -312,7 +312,7 @@ struct FInvertArgs {
     double dk;
 };
 
-struct InvIn { cd q1, q2; double fl; };
+struct InvIn { cd q1, q2; double fl, flp; };
 
 // ---- _invert + _calc_rel_vorticity in spectral space + the inverse radix stage of u + i v and q + i qw
 template <int N, bool HASW>
@@ -344,7 +344,10 @@ __global__ void __launch_bounds__(256, 2) k_finvert(FInvertArgs a) {
             const int ky = t.fam + M * q, kyp = (N - ky) & (N - 1);
             in.q1 = __ldg(&a.i.qh[i0 + (size_t)q * M * N]);
             in.q2 = __ldg(&a.i.qh[(size_t)kyp * N + colp]);
-            if (HASW) in.fl = __ldg(&a.i.filtr[i0 + (size_t)q * M * N]);
+            if (HASW) {
+                in.fl = __ldg(&a.i.filtr[i0 + (size_t)q * M * N]);
+                in.flp = a.i.filtr_sym ? in.fl : __ldg(&a.i.filtr[(size_t)kyp * N + colp]);
+            }
         };
         constexpr int D = FusedDepth<1>::INV;
         InvIn in[D];
@@ -360,14 +363,16 @@ __global__ void __launch_bounds__(256, 2) k_finvert(FInvertArgs a) {
             const double wv2 = __dadd_rn(__dmul_rn(k1, k1), __dmul_rn(l1, l1));
             const double wv2i = (wv2 != 0.0) ? 1.0 / wv2 : 0.0;
             const cd Hq = make_double2(0.5 * (e.q1.x + e.q2.x), 0.5 * (e.q1.y - e.q2.y));   // Herm(qh)(K)
-            cd qw = make_double2(0.0, 0.0);
+            cd qw = make_double2(0.0, 0.0), qwr = qw;      // Hermitian part (enters p, qw) / raw element (stored as qwh)
             if (HASW) {
                 const cd W1 = xs[q * 256 + tid], W2 = xs[fused_qp(t, q) * 256 + t.ptid];
                 const cd A = make_double2(0.5 * (W1.x + W2.x), 0.5 * (W1.y - W2.y));     // fft(|phi|^2)(K)
                 cd Jc = make_double2(a.i.inv_jscale * 0.5 * (W1.y + W2.y), a.i.inv_jscale * -0.5 * (W1.x - W2.x));
                 if (ky == 0 && t.col == 0) Jc = make_double2(0.0, 0.0);
-                qw.x = 0.5 * (0.5 * (-wv2 * A.x) + Jc.x) / a.i.f * e.fl;
-                qw.y = 0.5 * (0.5 * (-wv2 * A.y) + Jc.y) / a.i.f * e.fl;
+                const double bx = 0.5 * (0.5 * (-wv2 * A.x) + Jc.x) / a.i.f, by = 0.5 * (0.5 * (-wv2 * A.y) + Jc.y) / a.i.f;
+                const double fs = 0.5 * (e.fl + e.flp);
+                qw.x = bx * fs; qw.y = by * fs;
+                qwr.x = bx * e.fl; qwr.y = by * e.fl;
             }
             const cd ph1 = make_double2(wv2i * qw.x - wv2i * Hq.x, wv2i * qw.y - wv2i * Hq.y);
             {
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(256, 2) k_finvert(FInvertArgs a) {
                 s[SI_PQ] += r;
             }
             a.i.ph[i1] = ph1;
-            if (a.i.qwh) a.i.qwh[i1] = qw;
+            if (a.i.qwh) a.i.qwh[i1] = qwr;
             u[q] = make_double2(Hq.x - qw.y, Hq.y + qw.x);         // qs(K) = Herm(qh) + i qwh
         }
         if (HASW) __syncthreads();

@@ -18,6 +18,7 @@
 #include "kernels_family.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_qg.cuh"
+#include "kernels_ic.cuh"
 
 static std::string g_create_error;
 
@@ -663,6 +664,7 @@ static int invert_family(niwqg_handle* h, bool keep_qwh = true) {
     InvertArgs ia{};
     ia.g = h->g;
     ia.flags = h->flags; ia.f = h->p.f; ia.qh = h->qh[h->cq]; ia.filtr = h->filtr;
+    ia.filtr_sym = (h->p.use_filter || !h->p.dealias) ? 1 : 0;
     ia.ph = h->ph; ia.qs = h->qs;
     if (h->flags & MF_WAVE_PV) {
         { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
@@ -762,6 +764,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         // _invert(); _calc_rel_vorticity(); u, v
         FInvertArgs ia{};
         ia.i.g = h->g; ia.i.flags = h->flags; ia.i.f = h->p.f; ia.i.qh = h->qh[h->cq]; ia.i.filtr = h->filtr;
+        ia.i.filtr_sym = (h->p.use_filter || !h->p.dealias) ? 1 : 0;
         ia.i.ph = h->ph; ia.i.qs = h->qs; ia.i.W = h->T[0]; ia.i.qwh = (wave && st == 4) ? h->qwh : nullptr;
         ia.i.inv_jscale = 1.0 / h->jscale; ia.i.partials = h->part;
         ia.T = h->T[0]; ia.out_uv = h->T[1]; ia.out_qs = h->T[2]; ia.twc = h->twc; ia.dk = h->dk;
@@ -1302,10 +1305,9 @@ __global__ void k_set_scalar_from_sum(double* scal, int slot, const double* sums
     if (threadIdx.x == 0) scal[(size_t)m * NIWQG_S_COUNT + slot] = factor * sums[(size_t)m * K + idx];
 }
 
-int niwqg_set_q(niwqg_handle* h, const double* q, int on_device) {
-    CK(cudaSetDevice(h->p.device));
+// set_q once the physical q sits in h->rscratch in the device layout
+static int seed_q(niwqg_handle* h) {
     const size_t n = (size_t)h->B * h->npts;
-    { int r0 = upload_phys<double>(h, q, h->rscratch, n, on_device); if (r0) return r0; }
     const double M2 = h->Mg * h->Mg;
     if (h->qg) {
         // qh = rfft2(q): full c2c of the real field, keep columns 0..N/2 (QGModel.py:516-518)
@@ -1373,11 +1375,15 @@ __global__ void k_phi2_sum(const cd* __restrict__ phi, size_t npts, double* part
     block_reduce_store<1>(s, partials);
 }
 
-int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
-    if (h->qg) { h->err = "set_phi: QGModel has no wave field"; return -1; }
+int niwqg_set_q(niwqg_handle* h, const double* q, int on_device) {
     CK(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->B * h->npts;
-    { int r0 = upload_phys<cd>(h, phi, h->phi, n, on_device); if (r0) return r0; }
+    { int r0 = upload_phys<double>(h, q, h->rscratch, n, on_device); if (r0) return r0; }
+    return seed_q(h);
+}
+
+// set_phi once the physical phi sits in h->phi in the device layout
+static int seed_phi(niwqg_handle* h) {
     FFT(h->phi, h->phih[h->cp], false, PRO_NONE, h->B);
     int r = pe_niw_refresh(h, h->sumsX);
     if (r) return r;
@@ -1397,6 +1403,70 @@ int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
     }
     h->phi_set = true;
     return 0;
+}
+
+int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
+    if (h->qg) { h->err = "set_phi: QGModel has no wave field"; return -1; }
+    CK(cudaSetDevice(h->p.device));
+    const size_t n = (size_t)h->B * h->npts;
+    { int r0 = upload_phys<cd>(h, phi, h->phi, n, on_device); if (r0) return r0; }
+    return seed_phi(h);
+}
+
+int niwqg_ic(niwqg_handle* h, int kind, const double* prm, int nprm, const double* rand01) {
+    CK(cudaSetDevice(h->p.device));
+    const IcGeom g{h->N, h->nyl, h->rank * h->nyl, h->deintC, h->deintM, h->p.L};
+    const dim3 grid = pw_grid(h);
+    auto need = [&](int n) { if (nprm < n) { h->err = "ic: too few parameters"; return false; } return true; };
+    switch (kind) {
+        case NIWQG_IC_LAMB_DIPOLE: {
+            if (!need(2)) return -1;
+            k_ic_lamb<<<grid, NIWQG_PW_THREADS, 0, h->stream>>>(g, prm[0], prm[1], h->rscratch);
+            CK(cudaGetLastError());
+            h->launches++;
+            return seed_q(h);
+        }
+        case NIWQG_IC_WAVEPACKET: case NIWQG_IC_PLANEWAVE: case NIWQG_IC_UNIFORM: {
+            if (h->qg) { h->err = "ic: QGModel has no wave field"; return -1; }
+            double k = 0, l = 0, R = 1, x0 = 0, y0 = 0, phase = 0;
+            if (kind == NIWQG_IC_WAVEPACKET) { if (!need(5)) return -1; k = prm[0]; l = prm[1]; R = prm[2]; x0 = prm[3]; y0 = prm[4]; }
+            else if (kind == NIWQG_IC_PLANEWAVE) { if (!need(3)) return -1; k = prm[0]; l = prm[1]; phase = prm[2]; }
+            else { if (!need(2)) return -1; k = prm[0]; l = prm[1]; }
+            k_ic_phi<<<grid, NIWQG_PW_THREADS, 0, h->stream>>>(g, kind - NIWQG_IC_WAVEPACKET, k, l, R, x0, y0, phase, h->phi);
+            CK(cudaGetLastError());
+            h->launches++;
+            return seed_phi(h);
+        }
+        case NIWQG_IC_MCWILLIAMS: case NIWQG_IC_DANIOUX: {
+            // random red spectrum (InitialConditions.py:4-41, :43-75) through the model's own transforms
+            if (!need(3)) return -1;
+            if (h->qg || h->nranks > 1 || h->B != 1) { h->err = "ic: random spectra need a single-GPU, single-member c2c model"; return -1; }
+            const int N = h->N;
+            const double M2 = h->Mg * h->Mg;
+            const double* rnd = nullptr;
+            if (rand01) {       // the caller's uniform numbers (np.random.rand(N, N)): parity with the host generator
+                CK(cudaMemcpyAsync(h->P2, rand01, h->npts * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                rnd = (const double*)h->P2;
+            }
+            k_ic_spectrum<<<grid, NIWQG_PW_THREADS, 0, h->stream>>>(N, h->dk, kind == NIWQG_IC_MCWILLIAMS ? 0 : 1, prm[0], rnd,
+                                                                    (unsigned long long)prm[2], h->P1);
+            CK(cudaGetLastError());
+            FFT(h->P1, h->P1, true, PRO_NONE, 1);                 // ph = fft(ifft(ph).real)
+            k_ic_real<<<grid, NIWQG_PW_THREADS, 0, h->stream>>>(h->P1, h->npts);
+            CK(cudaGetLastError());
+            FFT(h->P1, h->P1, false, PRO_NONE, 1);
+            k_ic_energy<<<grid, NIWQG_PW_THREADS, 0, h->stream>>>(N, h->dk, h->P1, h->part);
+            CK(cudaGetLastError());
+            FIN(1, h->sumsX);
+            k_ic_scale<<<grid, NIWQG_PW_THREADS, 0, h->stream>>>(N, h->dk, prm[1], M2, h->sumsX, h->P1);
+            CK(cudaGetLastError());
+            FFT(h->P1, h->P1, true, PRO_NONE, 1, EPI_REAL_OUT, h->rscratch);    // q = ifft(-wv2 pih).real, device layout
+            h->launches += 4;
+            return seed_q(h);
+        }
+    }
+    h->err = "ic: unknown kind";
+    return -1;
 }
 
 int niwqg_set_c(niwqg_handle* h, const double* c, int on_device) {

@@ -21,6 +21,20 @@ CASES = {
     "qg_lamb64_filt": ("qg", 64, True, 2, 20, "lamb"),
     "qg_lamb128_nofilt_100": ("qg", 128, False, 1, 100, "lamb"),
     "qg_scalar64_nofilt": ("qgc", 64, False, 1, 20, "lamb"),
+    # parameter branches no other case touches (constructor keywords in EXTRA below)
+    "coupled_lamb64_diss": ("coupled", 64, True, 1, 10, "lamb"),       # nu4w, mu, muw != 0 (Kernel.py:688-689, :646-652)
+    "coupled_lamb64_dealias": ("coupled", 64, False, 2, 10, "lamb"),   # 2/3-rule mask (Kernel.py:277-281)
+    "uncoupled_lamb64_diss": ("uncoupled", 64, True, 2, 10, "lamb"),   # nu4w != 0 without the wave PV
+    "ql_lamb64_diss": ("ql", 64, True, 2, 10, "lamb"),                 # nu4w != 0 on the physical-space budget path
+    "qg_lamb64_beta": ("qg", 64, True, 2, 20, "lamb"),                 # beta != 0 (QGModel.py:428)
+}
+
+EXTRA = {
+    "coupled_lamb64_diss": dict(nu4w=2.e11, mu=2.e-8, muw=3.e-8),
+    "coupled_lamb64_dealias": dict(dealias=True),
+    "uncoupled_lamb64_diss": dict(nu4w=2.e11, muw=3.e-8),
+    "ql_lamb64_diss": dict(nu4w=2.e11, mu=2.e-8, muw=3.e-8),
+    "qg_lamb64_beta": dict(beta=2.e-11, mu=1.e-8),
 }
 
 

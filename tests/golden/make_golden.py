@@ -78,6 +78,12 @@ CASES = [
     ("qg_lamb64_filt", "qg", 64, True, 2, 20, "lamb"),
     ("qg_lamb128_nofilt_100", "qg", 128, False, 1, 100, "lamb"),
     ("qg_scalar64_nofilt", "qgc", 64, False, 1, 20, "lamb"),
+    # parameter branches (keywords in tests/cases.py:EXTRA)
+    ("coupled_lamb64_diss", "coupled", 64, True, 1, 10, "lamb"),
+    ("coupled_lamb64_dealias", "coupled", 64, False, 2, 10, "lamb"),
+    ("uncoupled_lamb64_diss", "uncoupled", 64, True, 2, 10, "lamb"),
+    ("ql_lamb64_diss", "ql", 64, True, 2, 10, "lamb"),
+    ("qg_lamb64_beta", "qg", 64, True, 2, 20, "lamb"),
 ]
 
 
@@ -86,6 +92,9 @@ def run_case(ctor, ic, name, model, nx, use_filter, tdiags, nsteps, icname):
     kw, U0, k0 = lamb_params(nx, use_filter, tdiags, nsteps, qg=qg)
     if model == "qgc":
         kw.update(passive_scalar=True, nu4c=3.e9 * (128 / nx) ** 4, nuc=0)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from cases import EXTRA
+    kw.update(EXTRA.get(name, {}))
     m = ctor["qg" if qg else model](**kw)
     if icname == "lamb":
         q = ic.LambDipole(m, U=U0, R=2 * np.pi / k0)
@@ -153,7 +162,10 @@ def reference_tests_known_answers(ctor):
 
 if __name__ == "__main__":
     ctor, ic = import_reference()
+    only = sys.argv[1:]          # optional: regenerate just these cases
     for case in CASES:
-        run_case(ctor, ic, *case)
-    coefficient_case(ctor)
-    reference_tests_known_answers(ctor)
+        if not only or case[0] in only:
+            run_case(ctor, ic, *case)
+    if not only:
+        coefficient_case(ctor)
+        reference_tests_known_answers(ctor)

@@ -1,0 +1,98 @@
+"""Device-side initial conditions (csrc/kernels_ic.cuh, niwqg_ic) against the host generators of
+niwqg_b200/InitialConditions.py, which reproduce niwqg/InitialConditions.py bit for bit (tests/test_host_cpu.py)."""
+import logging
+import time
+
+import numpy as np
+import pytest
+
+from cases import lamb_params, rel_l2
+
+pytestmark = pytest.mark.gpu
+logging.disable(logging.CRITICAL)
+
+
+def _pair(nx, cls=None):
+    from niwqg_b200 import CoupledModel
+    kw, U0, k0 = lamb_params(nx, True, 10 ** 9, 1)
+    cls = cls or CoupledModel.Model
+    return cls(**kw), cls(**kw), U0, k0
+
+
+@pytest.mark.parametrize("nx", [128, 512])
+def test_lamb_dipole_on_device(nx):
+    from niwqg_b200 import InitialConditions as ic
+    a, b, U0, k0 = _pair(nx)
+    q = ic.LambDipole(a, U=U0, R=2 * np.pi / k0)
+    a.set_q(q)
+    assert ic.LambDipole(b, U=U0, R=2 * np.pi / k0, on_device=True) is None
+    # j0 / j1 of CUDA vs scipy differ in the last bits; fields are compared on the scale of the field
+    assert np.max(np.abs(b.q - a.q)) <= 1e-13 * np.max(np.abs(q))
+    assert rel_l2(b.qh, a.qh) < 1e-13 and rel_l2(b.ph, a.ph) < 1e-13
+    assert abs(a.Ke - b.Ke) <= 1e-13 * abs(a.Ke)
+
+
+def test_lamb_dipole_on_device_qg():
+    from niwqg_b200 import InitialConditions as ic, QGModel
+    kw, U0, k0 = lamb_params(128, True, 10 ** 9, 1, qg=True)
+    a, b = QGModel.Model(**kw), QGModel.Model(**kw)
+    a.set_q(ic.LambDipole(a, U=U0, R=2 * np.pi / k0))
+    ic.LambDipole(b, U=U0, R=2 * np.pi / k0, on_device=True)
+    assert np.max(np.abs(b.q - a.q)) <= 1e-13 * np.max(np.abs(a.q)) and rel_l2(b.qh, a.qh) < 1e-13
+
+
+@pytest.mark.parametrize("gen", ["McWilliams1984", "Danioux2015"])
+def test_random_spectrum_on_device_matches_host_for_the_same_phases(gen):
+    from niwqg_b200 import InitialConditions as ic
+    nx = 512
+    a, b, U0, k0 = _pair(nx)
+    np.random.seed(7)
+    q = getattr(ic, gen)(a, k0=k0, E=U0 ** 2 / 2)
+    a.set_q(q)
+    np.random.seed(7)                           # the same draw of np.random.rand(N, N), handed to the device generator
+    getattr(ic, gen)(b, k0=k0, E=U0 ** 2 / 2, on_device=True)
+    assert rel_l2(b.q, q) < 1e-12 and rel_l2(b.qh, a.qh) < 1e-12
+    assert abs(0.5 * (np.abs(b.u) ** 2 + np.abs(b.v) ** 2).mean() - U0 ** 2 / 2) < 1e-4 * U0 ** 2      # normalised to E (up to the Nyquist modes .real drops)
+    # Philox phases: a different realisation with the same spectrum and energy, reproducible for a given seed
+    c, d, _, _ = _pair(nx)
+    getattr(ic, gen)(c, k0=k0, E=U0 ** 2 / 2, on_device=True, seed=1234)
+    getattr(ic, gen)(d, k0=k0, E=U0 ** 2 / 2, on_device=True, seed=1234)
+    assert np.array_equal(c.q, d.q) and rel_l2(c.q, q) > 0.1
+    assert abs(c.Ke - a.Ke) < 1e-9 * a.Ke
+
+
+def test_wave_generators_on_device():
+    from niwqg_b200 import InitialConditions as ic
+    nx = 256
+    a, b, U0, k0 = _pair(nx)
+    for gen, kw in (("WavePacket", dict(k=3 * k0, l=-2 * k0, R=a.L / 7, x0=0.4 * a.L, y0=0.55 * a.L)),
+                    ("PlaneWave", dict(k=5 * k0 / 10, l=9 * k0 / 10, phase=0.3))):
+        phi = getattr(ic, gen)(a, **kw)
+        a.set_phi(phi)
+        getattr(ic, gen)(b, on_device=True, **kw)
+        assert np.max(np.abs(b.phi - phi)) <= 1e-12 * np.max(np.abs(phi)), gen      # sincos of arguments up to ~1e3
+        assert rel_l2(b.phih, a.phih) < 1e-12
+        assert abs(a.Kw - b.Kw) <= 1e-12 * abs(a.Kw)
+    ic.UniformWave(b, phi0=0.1 * (1 + 1j))
+    assert np.array_equal(b.phi, np.full((nx, nx), 0.1 * (1 + 1j)))
+
+
+def test_8192_model_and_device_ic_in_seconds():
+    """Config 4 set-up: constructing the 8192^2 model (lazy host grids, tables generated on the device) and seeding it
+    with the Lamb dipole + uniform wave on the device takes seconds and no whole-grid host array."""
+    from niwqg_b200 import CoupledModel, InitialConditions as ic
+    kw, U0, k0 = lamb_params(8192, True, 10 ** 9, 1)
+    t0 = time.perf_counter()
+    m = CoupledModel.Model(**kw)
+    ic.LambDipole(m, U=U0, R=2 * np.pi / k0, on_device=True)
+    ic.UniformWave(m, phi0=(1 + 1j) * (2 * U0) / np.sqrt(2))
+    m._h.sync()
+    dt = time.perf_counter() - t0
+    assert not any(k in m.__dict__ for k in ("x", "y", "k", "l", "wv2", "wv", "wv4", "wv2i", "ik", "il"))
+    # same state as the host path (checked on the kinetic energy and a strip of q)
+    m2 = CoupledModel.Model(**kw)
+    q = ic.LambDipole(m2, U=U0, R=2 * np.pi / k0)
+    m2.set_q(q); m2.set_phi((np.ones_like(q) + 1j) * (2 * U0) / np.sqrt(2))
+    assert abs(m.Ke - m2.Ke) <= 1e-12 * abs(m2.Ke) and abs(m.Kw - m2.Kw) <= 1e-12 * abs(m2.Kw)
+    assert np.max(np.abs(m.q[4000:4200] - q[4000:4200])) <= 1e-13 * np.abs(q).max()
+    assert dt < 5.0, dt

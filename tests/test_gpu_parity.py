@@ -6,7 +6,7 @@ steps (fp64 throughout); budgets are compared relative to their own magnitude.""
 import numpy as np
 import pytest
 
-from cases import CASES, lamb_params, load_golden, rel_l2
+from cases import CASES, EXTRA, lamb_params, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,7 @@ def build_cuda(name, **over):
     kw, U0, k0 = lamb_params(nx, use_filter, tdiags, nsteps, qg=qg)
     if model == "qgc":
         kw.update(passive_scalar=True, nu4c=3.e9 * (128 / nx) ** 4, nuc=0)
+    kw.update(EXTRA.get(name, {}))
     kw.update(over)
     m = _models()[model](**kw)
     if icname == "lamb":
@@ -95,8 +96,22 @@ def test_tables_match_reference():
     m = CoupledModel.Model(**kw)
     for n in ["expch", "expch_h", "expchw", "expch_hw", "Qh", "Qhw", "filtr"]:
         assert np.max(np.abs(getattr(m, n) - g[n])) <= 1e-13 * np.max(np.abs(g[n])), n
-    for n in ["f0", "fab", "fc", "f0w", "fabw", "fcw"]:
-        assert np.max(np.abs(getattr(m, n) - g[n])) <= 1e-7 * np.max(np.abs(g[n])), n
+    # f0, fab, fc: 32-point contour means of (...)/LR^3 with LR = c dt + r_j on the unit circle.  Where the circle
+    # passes close to the origin (|c dt| ~ 1) the terms are huge and cancel, and BOTH implementations lose digits
+    # there, so the comparison is split: every wavenumber whose contour stays >= 0.1 away from the origin must
+    # agree to 1e-13, the others (a thin shell |c dt| ~ 1) to 1e-7; their number and worst error are reported.
+    r = np.exp(2j * np.pi * (np.arange(1, 33) / 32.))
+    for tabs, cname in ((("f0", "fab", "fc"), "c_q"), (("f0w", "fabw", "fcw"), "c_phi")):
+        ch = np.log(g["expch" if cname == "c_q" else "expchw"].astype(complex))     # c dt (principal branch: |Im| < pi here)
+        dist = np.min(np.abs(ch[..., None] + r), axis=-1)
+        far = dist > 0.1
+        assert far.mean() > 0.9
+        for n in tabs:
+            err = np.abs(getattr(m, n) - g[n]) / np.max(np.abs(g[n]))
+            print("%s: %d of %d points within 0.1 of the contour, max err there %.1e, elsewhere %.1e"
+                  % (n, (~far).sum(), far.size, err[~far].max() if (~far).any() else 0.0, err[far].max()))
+            assert err[far].max() <= 1e-13, n
+            assert err.max() <= 1e-7, n
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -165,7 +180,8 @@ def _diag_check(name, dn, got, ref, g):
 
 @pytest.mark.parametrize("name", ["coupled_lamb64_filt", "coupled_lamb64_nofilt", "uncoupled_lamb64_filt", "ql_lamb64_filt",
                                   "ybj_lamb64_filt", "coupled_rand64_filt", "coupled_lamb128_nofilt_100",
-                                  "qg_lamb64_filt", "qg_scalar64_nofilt"])
+                                  "qg_lamb64_filt", "qg_scalar64_nofilt", "coupled_lamb64_diss", "coupled_lamb64_dealias",
+                                  "uncoupled_lamb64_diss", "ql_lamb64_diss", "qg_lamb64_beta"])
 def test_diagnostics_series_match_reference(name):
     g = load_golden(name)
     m = build_cuda(name)
@@ -217,3 +233,29 @@ def test_seeding_order_semantics_F5():
     b = CoupledModel.Model(**kw)
     b.set_q(q); b.set_phi(phi); b._step_etdrk4()
     assert rel_l2(b.phi, o.phi) > 1e-7        # the order matters, as in the reference
+
+
+@pytest.mark.parametrize("model", ["coupled", "qg"])
+def test_run_with_snapshots_generator(model):
+    """Kernel.run_with_snapshots (niwqg/Kernel.py:161-181; QGModel.py:175-195): yields t every tsnapint while stepping to
+    tmax; the state after the generator is exhausted equals a plain run()."""
+    import logging
+    logging.disable(logging.CRITICAL)
+    from niwqg_b200 import CoupledModel, QGModel
+    from oracle import niwqg_oracle as orc
+    qg = model == "qg"
+    kw, U0, k0 = lamb_params(64, True, 5, 12, qg=qg)
+    cls = QGModel.Model if qg else CoupledModel.Model
+    a, b = cls(**kw), cls(**kw)
+    q = orc.lamb_dipole(a, U=U0, R=2 * np.pi / k0)
+    for mdl in (a, b):
+        mdl.set_q(q)
+        if not qg:
+            mdl.set_phi((np.ones_like(q) + 1j) * (2 * U0) / np.sqrt(2))
+    snaps = list(a.run_with_snapshots(tsnapstart=0., tsnapint=3 * a.dt))
+    b.run()
+    assert a.tc == b.tc == 12
+    assert np.array_equal(a.q, b.q)
+    # reference semantics: yield t after every step with tc % ceil(tsnapint / dt) == 0 (and t >= tsnapstart)
+    assert len(snaps) == 4
+    assert np.allclose(snaps, np.array([3, 6, 9, 12]) * a.dt, rtol=1e-12)

@@ -5,7 +5,7 @@ import os, sys
 import numpy as np
 import pytest
 
-from cases import CASES, lamb_params, load_golden
+from cases import CASES, EXTRA, lamb_params, load_golden
 from oracle import niwqg_oracle as orc
 
 
@@ -16,8 +16,10 @@ def build_oracle(name):
     if qg:
         if model == "qgc":
             kw.update(passive_scalar=True, nu4c=3.e9 * (128 / nx) ** 4, nuc=0)
+        kw.update(EXTRA.get(name, {}))
         m = orc.QGOracle(**kw)
     else:
+        kw.update(EXTRA.get(name, {}))
         m = orc.NIWQGOracle(model=model, **kw)
     if icname == "lamb":
         q = orc.lamb_dipole(m, U=U0, R=2 * np.pi / k0)
