@@ -146,6 +146,12 @@ int niwqg_get_scalars(niwqg_handle* h, double* out);
  * (host if on_device==0).  bytes must equal the field's size. */
 int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t bytes, int on_device);
 size_t niwqg_field_bytes(const niwqg_handle* h, int field);
+/* The same copy to a (pinned) host buffer, queued on the handle's copy stream behind the work already issued: returns
+ * at once, so the caller can start the next uploads while the result is still on its way (full-duplex PCIe).  dst is
+ * valid after niwqg_wait_transfers (or niwqg_sync).  One real and one complex field can be in flight at a time; a
+ * further request waits for the staging buffer it needs. */
+int niwqg_get_field_async(niwqg_handle* h, int field, int member, void* dst, size_t bytes);
+int niwqg_wait_transfers(niwqg_handle* h);
 
 /* the FFT backend seam (niwqg/Kernel.py:553-566, niwqg/QGModel.py:536-552): one N x N
  * transform with numpy conventions, host buffers. */

@@ -17,7 +17,7 @@ import numpy as np
 def _device(model, kind, params, rand01=None):
     model._h.ic(kind, params, rand01)
     if kind in ("LambDipole", "McWilliams1984", "Danioux2015") and hasattr(model, "Ke") and not getattr(model, "_is_qg", False):
-        model.ke = model.Ke            # Kernel.set_q side effect (niwqg/Kernel.py:535)
+        model.ke = None                # Kernel.set_q side effect (niwqg/Kernel.py:535): served from the device on first read
     return None
 
 

@@ -80,6 +80,7 @@ class Kernel(object):
     """
 
     _model_id = None     # set by subclasses
+    _ke = None
 
     # device-backed attributes (names of the reference's numpy arrays)
     q = _DeviceField("Q"); qh = _DeviceField("QH"); p = _DeviceField("P"); ph = _DeviceField("PH")
@@ -247,9 +248,21 @@ class Kernel(object):
 
     # ---------------------------------------------------------------- seeding
     def set_q(self, q):
-        """niwqg/Kernel.py:520-535 (inverts with the current phi, F5)."""
+        """niwqg/Kernel.py:520-535 (inverts with the current phi, F5).  ``self.ke = Ke`` of the reference is served on
+        first read (property below): reading it here would make the host wait for the inversion, which otherwise runs
+        on the device while the caller already uploads phi."""
         self._h.set_q(q)
-        self.ke = self.Ke
+        self._ke = None
+
+    @property
+    def ke(self):
+        if self._ke is None:
+            self._ke = self.Ke
+        return self._ke
+
+    @ke.setter
+    def ke(self, value):
+        self._ke = value
 
     def set_phi(self, phi):
         """niwqg/Kernel.py:538-551 (does not re-invert, F5)."""

@@ -39,6 +39,7 @@ EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
            "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id", "niwqg_ic",
+           "niwqg_get_field_async", "niwqg_wait_transfers",
            "niwqg_ipc_export", "niwqg_ipc_import", "niwqg_ipc_disable"]
 
 
@@ -76,6 +77,8 @@ def load():
     for n in ("niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars"):
         getattr(lib, n).argtypes = [vp, vp]
     lib.niwqg_get_field.argtypes = [vp, ip, ip, vp, C.c_size_t, ip]
+    lib.niwqg_get_field_async.argtypes = [vp, ip, ip, vp, C.c_size_t]
+    lib.niwqg_wait_transfers.argtypes = [vp]
     lib.niwqg_field_bytes.argtypes = [vp, ip]
     lib.niwqg_field_bytes.restype = C.c_size_t
     lib.niwqg_fft2.argtypes = [vp, vp, vp, ip]
@@ -222,20 +225,19 @@ class Handle(object):
                 raise ValueError("expected %d values, got %d" % (want, a.size))
         return a
 
+    # The library returns from set_* once the host array has been copied (the caller may reuse it); the inversion and
+    # transforms that follow stay queued on the handle's stream, and every later call is ordered behind them.
     def set_q(self, q):
         a = self._host(q, np.float64)
         self._ck(self.lib.niwqg_set_q(self.h, a.ctypes.data, 0))
-        self.sync()
 
     def set_phi(self, phi):
         a = self._host(phi, np.complex128)
         self._ck(self.lib.niwqg_set_phi(self.h, a.ctypes.data, 0))
-        self.sync()
 
     def set_c(self, c):
         a = self._host(c, np.float64)
         self._ck(self.lib.niwqg_set_c(self.h, a.ctypes.data, 0))
-        self.sync()
 
     IC_KINDS = {"LambDipole": 0, "McWilliams1984": 1, "Danioux2015": 2, "WavePacket": 3, "PlaneWave": 4, "Uniform": 5}
 
@@ -277,10 +279,17 @@ class Handle(object):
         self._ck(self.lib.niwqg_profile(self.h, int(bool(enable)), ms.ctypes.data, cnt.ctypes.data))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 
-    def field_into(self, name, out, member=0):
-        """Copy one member's field into a caller-provided (e.g. pinned) host array."""
-        self._ck(self.lib.niwqg_get_field(self.h, F[name], member, out.ctypes.data, out.nbytes, 0))
+    def field_into(self, name, out, member=0, wait=True):
+        """Copy one member's field into a caller-provided (e.g. pinned) host array.  wait=False queues the copy on the
+        handle's copy stream and returns at once; the array is valid after wait_transfers() (or sync())."""
+        if wait:
+            self._ck(self.lib.niwqg_get_field(self.h, F[name], member, out.ctypes.data, out.nbytes, 0))
+        else:
+            self._ck(self.lib.niwqg_get_field_async(self.h, F[name], member, out.ctypes.data, out.nbytes))
         return out
+
+    def wait_transfers(self):
+        self._ck(self.lib.niwqg_wait_transfers(self.h))
 
     def launch_count(self):
         return int(self.lib.niwqg_launch_count(self.h))

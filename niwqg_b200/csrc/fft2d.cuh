@@ -246,6 +246,13 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+// linear bulk copy global -> shared (cp.async.bulk, SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+
 // L2 prefetch of the tile that the CTA `pf_groups` line groups ahead will load: the DRAM latency of that tile
 // is paid while the tiles in between are transformed, so a CTA's own loads are (mostly) L2 hits.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -291,7 +298,7 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
     bool tma_done = false;
     if constexpr (COL && NAT && C == 1 && M >= 256) {
-        if (a.tma_in) {
+        if (a.tma_in & 1) {
             // the whole W x M tile by TMA: boxes of 256 rows x (W*16) bytes land densely ([row][W]) in the exchange buffer
             const unsigned bar = smem_u32(smtw + TL::TWLEN);
             if (tid == 0) {
@@ -309,6 +316,28 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
             mbar_wait(bar, 0);
 #pragma unroll
             for (int e = 0; e < fftc::E; ++e) v[e] = smem[(size_t)(j + e * TL::TPF) * W + w];
+            __syncthreads();        // the landing area is the exchange buffer of the stages
+            tma_done = true;
+        }
+    }
+    if constexpr (!COL && NAT && C == 1 && M * W == 4096) {
+        if ((a.tma_in & 2) && a.pro != PRO_REAL_IN) {
+            // row pass, one tile: the W lines of the group are one contiguous 64 KB block - ONE bulk copy into the
+            // exchange buffer instead of 16 LDG.128 per thread (A/B against the register loads: profiles/r02_*)
+            const unsigned bar = smem_u32(smtw + TL::TWLEN);
+            if (tid == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(bar, (unsigned)(W * M * sizeof(cd)));
+                bulk_load(smem_u32(smem), (const cd*)a.in + mbase + (size_t)group * W * N, (unsigned)(W * M * sizeof(cd)), bar);
+            }
+            for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+            mbar_wait(bar, 0);
+#pragma unroll
+            for (int e = 0; e < fftc::E; ++e) v[e] = smem[(size_t)w * M + j + e * TL::TPF];
             __syncthreads();        // the landing area is the exchange buffer of the stages
             tma_done = true;
         }
@@ -632,11 +661,15 @@ template <int N, int R, int W>
 static cudaError_t launch_col3(const FftArgs& a, void* scratch, int batch, cudaStream_t st) {
     constexpr int M = N / R;
     using TL = Tile<M, W, R, true>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is per DEVICE: one flag per device ordinal (a handle may be
+    // created on any device of the process)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_fft_colsub<M, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev < 64) attr_set[dev] = true;
     }
     FftArgs b = a;               // pass A: prologue + conj on load, no epilogue
     b.out = scratch; b.epi = EPI_NONE; b.scale = 1.0; b.scale_im = 1.0;
@@ -673,8 +706,10 @@ static cudaError_t launch_pass_g(const FftArgs& a, int batch, cudaStream_t st) {
     using TL = Tile<M, W, C, COL>;
     constexpr size_t HALF_SM = 116 * 1024;      // more than half of the 227 KB an SM can give to CTAs
     constexpr size_t SMEM_MAX = TL::SMEM > HALF_SM ? TL::SMEM : HALF_SM;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};     // per device ordinal (see launch_col3)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_fft_pass<M, W, C, COL, NAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SMEM_MAX);
         if (e != cudaSuccess) return e;
@@ -684,7 +719,7 @@ static cudaError_t launch_pass_g(const FftArgs& a, int batch, cudaStream_t st) {
             e = cudaFuncSetAttribute(k_fft_pass_dif<M, W, C, COL, NAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
             if (e != cudaSuccess) return e;
         }
-        attr_set = true;
+        if (dev < 64) attr_set[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((a.nlines / W) * C, batch, 1);
@@ -709,9 +744,9 @@ static cudaError_t launch_pass_g(const FftArgs& a, int batch, cudaStream_t st) {
     }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    b.tma_in = 0;
+    b.tma_in = (!COL && NAT) ? (a.tma_in & 2) : 0;      // bit 1: row tiles by one bulk copy (k_fft_pass)
     if constexpr (COL && NAT && C == 1 && M >= 256 && W * sizeof(cd) < 128) {   // full 128 B rows (W = 8) are as fast with LDG
-        if (a.tma_in && a.pro != PRO_REAL_IN) {
+        if ((a.tma_in & 1) && a.pro != PRO_REAL_IN) {
             // 2-D view of the input: inner dimension = one grid row as doubles, outer = all rows of all members
             static PFN_tmapEncodeTiled enc = tma_encoder();
             if (enc) {

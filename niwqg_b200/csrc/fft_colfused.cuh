@@ -66,11 +66,6 @@ __device__ __forceinline__ cd ld_stream(const cd* p) {     // read once: do not 
     asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 // ticket -> (kind, super-block, index): step t holds the producers of super-block t interleaved with the consumers of
 // super-block t - D
 template <int N, int CW, int REP>
@@ -250,10 +245,10 @@ template <int N, int CW> static size_t col_fused_ring_bytes(int nslot) { return 
 template <int N, int CW, int REP = 1>
 static cudaError_t launch_col_fused(const FftArgs& a, const ColFusedArgs& f, int nctas, cudaStream_t st) {
     using CF = ColFused<N, CW, REP>;
-    static bool attr_set[16] = {};
+    static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !attr_set[dev]) {
+    if (dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_col_fused<N, CW, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;

@@ -145,10 +145,10 @@ template <int N>
 static cudaError_t split_set_attrs() {
     constexpr int M = N / 16, W = 4096 / M;
     using TL = Tile<M, W, 16, true>;
-    static bool attr_set[16] = {};
+    static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !attr_set[dev]) {
+    if (dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_fft_colsub2<M, W, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_fft_colsub2<M, W, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);

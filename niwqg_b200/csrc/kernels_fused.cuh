@@ -401,10 +401,10 @@ __global__ void __launch_bounds__(256, 2) k_finvert(FInvertArgs a) {
 
 template <int N>
 static cudaError_t fused_set_attrs() {
-    static bool attr_set[16] = {};
+    static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 16 || attr_set[dev]) return cudaSuccess;
+    if (dev < 64 && attr_set[dev]) return cudaSuccess;
     const int sm = (int)FusedGeom<N>::XSMEM;
     cudaError_t e;
 #define NIWQG_ATTR(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)) != cudaSuccess) return e;
@@ -412,7 +412,7 @@ static cudaError_t fused_set_attrs() {
     NIWQG_ATTR((k_fstage_phi<N, 1>)) NIWQG_ATTR((k_fstage_phi<N, 2>)) NIWQG_ATTR((k_fstage_phi<N, 3>)) NIWQG_ATTR((k_fstage_phi<N, 4>))
     NIWQG_ATTR((k_finvert<N, true>))
 #undef NIWQG_ATTR
-    attr_set[dev] = true;
+    if (dev < 64) attr_set[dev] = true;
     return cudaSuccess;
 }
 

@@ -111,6 +111,16 @@ struct niwqg_handle {
     int split = 0;
     cd* T[3] = {nullptr, nullptr, nullptr};   // scratch arrays of the split path
     cd *tw_half = nullptr, *tw_m = nullptr;   // stage twiddles of the N/2-point rows and of the N/16-point column transforms
+    // host <-> device transfers of whole fields run on their own stream through staging buffers, so an upload overlaps the
+    // compute still queued on the main stream (set_phi's copy under set_q's inversion) and a download overlaps whatever
+    // the caller does next (niwqg_get_field_async: the next step's uploads)
+    cudaStream_t copy_stream = nullptr, copy_out = nullptr;     // uploads / downloads: separate streams, PCIe is full duplex
+    cudaEvent_t ev_up_done = nullptr, ev_up_free = nullptr, ev_dn_ready = nullptr, ev_dn_done[2] = {nullptr, nullptr};
+    bool up_free_rec = false, dn_done_rec[2] = {false, false};
+    void* stage_in = nullptr;                 // B * npts * 16 bytes
+    void* stage_out[2] = {nullptr, nullptr};  // one member: real (npts * 8) / complex (npts * 16)
+    double* pin = nullptr;                    // pinned host scratch for the scalars of diagnostics / status
+    int row_bulk = 1;           // split path: row tiles fetched by one bulk copy (cp.async.bulk; NIWQG_ROW_BULK=0: 16 LDG.128 per thread)
     int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
                                 // NIWQG_FUSED=0 runs the stage as launches of its own
     int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
@@ -258,6 +268,8 @@ static int split_rows(niwqg_handle* h, const void* in, void* out, int pro, int e
     a.in = in; a.out = out; a.pro = pro; a.epi = epi; a.tw = h->tw_half;
     a.nlines = 2 * h->N; a.pitch = Nh; a.mstride = (size_t)Nh * Nh; a.g = Grid{Nh, h->dk, Nh, Nh / 2, 0, 0};
     a.conj_in = 0; a.conj_out = conj_out ? 1 : 0; a.scale = sc; a.scale_im = conj_out ? -sc : sc;
+    a.tma_in = h->row_bulk ? 2 : 0;
+    a.pf_groups = 0;       // measured on 16384 lines of 4096: 0.362 ms without the L2 prefetch, 0.382 ms with it
     { PROF(PK_FFT_ROW); CK(launch_pass<false>(Nh, a, 1, h->stream)); }
     h->launches++;
     return 0;
@@ -966,27 +978,76 @@ static int qg_gamma_c(niwqg_handle* h) {
 // ---------------------------------------------------------------------------
 // physical arrays cross the ABI in natural x order; on the device they may be de-interleaved (k_deint)
 // ---------------------------------------------------------------------------
+static const size_t STAGED_BYTES = 32u << 20;      // transfers at least this large go through the copy stream
+
 template <typename T>
 static int upload_phys(niwqg_handle* h, const void* src, T* dst, size_t nelem, int on_device) {
-    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (h->deintC <= 1) { CK(cudaMemcpyAsync(dst, src, nelem * sizeof(T), kind, h->stream)); return 0; }
-    T* stage = (T*)h->P2;
-    CK(cudaMemcpyAsync(stage, src, nelem * sizeof(T), kind, h->stream));
-    k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(stage, dst, nelem, h->N, h->deintM, h->deintC, 1);
-    CK(cudaGetLastError());
-    h->launches++;
-    return 0;
-}
-template <typename T>
-static int download_phys(niwqg_handle* h, const T* src, void* dst, size_t nelem, int on_device, T* stage) {
-    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t bytes = nelem * sizeof(T);
+    if (on_device || bytes < STAGED_BYTES || !h->stage_in) {
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        T* to = (h->deintC <= 1) ? dst : (T*)h->P2;
+        CK(cudaMemcpyAsync(to, src, bytes, kind, h->stream));
+        if (!on_device) {                       // the caller may reuse its buffer when we return
+            CK(cudaEventRecord(h->ev_up_done, h->stream));
+            CK(cudaEventSynchronize(h->ev_up_done));
+        }
+        if (h->deintC > 1) {
+            k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>((const T*)h->P2, dst, nelem, h->N, h->deintM, h->deintC, 1);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+        return 0;
+    }
+    // host -> staging on the copy stream (as soon as the previous upload has been consumed), staging -> field on the
+    // main stream behind whatever is already queued there
+    if (h->up_free_rec) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_up_free, 0));
+    CK(cudaMemcpyAsync(h->stage_in, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->ev_up_done, h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_up_done, 0));
     if (h->deintC > 1) {
-        k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(src, stage, nelem, h->N, h->deintM, h->deintC, 0);
+        k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>((const T*)h->stage_in, dst, nelem, h->N, h->deintM, h->deintC, 1);
         CK(cudaGetLastError());
         h->launches++;
-        src = stage;
+    } else {
+        CK(cudaMemcpyAsync(dst, h->stage_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
     }
-    CK(cudaMemcpyAsync(dst, src, nelem * sizeof(T), kind, h->stream));
+    CK(cudaEventRecord(h->ev_up_free, h->stream));
+    h->up_free_rec = true;
+    CK(cudaEventSynchronize(h->ev_up_done));    // the caller may reuse its buffer when we return
+    return 0;
+}
+// field (device layout) -> caller.  async: returns once the copy is queued (niwqg_wait_transfers completes it)
+template <typename T>
+static int download_phys(niwqg_handle* h, const T* src, void* dst, size_t nelem, int on_device, T* stage, bool async = false) {
+    const size_t bytes = nelem * sizeof(T);
+    const int k = sizeof(T) == sizeof(cd) ? 1 : 0;
+    if (on_device || bytes < STAGED_BYTES || !h->stage_out[k]) {
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (h->deintC > 1) {
+            k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(src, stage, nelem, h->N, h->deintM, h->deintC, 0);
+            CK(cudaGetLastError());
+            h->launches++;
+            src = stage;
+        }
+        CK(cudaMemcpyAsync(dst, src, bytes, kind, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    T* so = (T*)h->stage_out[k];
+    if (h->dn_done_rec[k]) CK(cudaStreamWaitEvent(h->stream, h->ev_dn_done[k], 0));    // staging free again
+    if (h->deintC > 1) {
+        k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>(src, so, nelem, h->N, h->deintM, h->deintC, 0);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
+        CK(cudaMemcpyAsync(so, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(cudaEventRecord(h->ev_dn_ready, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_out, h->ev_dn_ready, 0));
+    CK(cudaMemcpyAsync(dst, so, bytes, cudaMemcpyDeviceToHost, h->copy_out));
+    CK(cudaEventRecord(h->ev_dn_done[k], h->copy_out));
+    h->dn_done_rec[k] = true;
+    if (!async) CK(cudaEventSynchronize(h->ev_dn_done[k]));
     return 0;
 }
 
@@ -1015,6 +1076,10 @@ int niwqg_destroy(niwqg_handle* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->copy_out) { cudaStreamSynchronize(h->copy_out); cudaStreamDestroy(h->copy_out); }
+    for (cudaEvent_t e : {h->ev_up_done, h->ev_up_free, h->ev_dn_ready, h->ev_dn_done[0], h->ev_dn_done[1]}) if (e) cudaEventDestroy(e);
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1034,7 +1099,15 @@ static int create_impl(niwqg_handle* h) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_up_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_up_free, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_dn_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_dn_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_dn_done[1], cudaEventDisableTiming));
     h->N = N; h->B = p.batch; h->model = p.model; h->qg = (p.model == NIWQG_MODEL_QG);
+    CK(cudaMallocHost((void**)&h->pin, ((size_t)p.batch * (NIWQG_S_COUNT + 64) + 64) * sizeof(double)));
     h->nranks = p.nranks > 1 ? p.nranks : 1;
     h->rank = h->nranks > 1 ? p.rank : 0;
     h->nyl = N / h->nranks; h->ncl = N / h->nranks;
@@ -1048,6 +1121,7 @@ static int create_impl(niwqg_handle* h) {
         const char* e = getenv("NIWQG_SPLIT");
         h->split = e ? (atoi(e) != 0) : (N == 8192);
         if (const char* f = getenv("NIWQG_FUSED")) h->fused = atoi(f);
+        if (const char* f = getenv("NIWQG_ROW_BULK")) h->row_bulk = atoi(f);
         if (h->split) { h->deintM = N / 2; h->deintC = 2; }
     }
     h->g = Grid{N, 2.0 * M_PI / p.L, h->ncl, h->ncl / 2, h->rank, h->nranks > 1 ? 1 : 0};
@@ -1192,6 +1266,11 @@ static int create_impl(niwqg_handle* h) {
     } else if (p.passive_scalar) {
         DA(h->chh[0], ssz); DA(h->chh[1], ssz); DA(h->y1c, ssz); DA(h->F0c, ssz); DA(h->Fabc, ssz);
     }
+    if (B * h->npts * sizeof(cd) >= STAGED_BYTES) {
+        DA(h->stage_in, B * h->npts * sizeof(cd));
+        DA(h->stage_out[0], h->npts * sizeof(double));
+        DA(h->stage_out[1], h->npts * sizeof(cd));
+    }
     DA(h->part, B * NIWQG_PW_BLOCKS * 16 * sizeof(double));
     DA(h->sumsD, B * 16 * sizeof(double)); DA(h->sumsE, B * 16 * sizeof(double)); DA(h->sumsX, B * 16 * sizeof(double));
     DA(h->sumsI, B * 16 * sizeof(double));
@@ -1283,6 +1362,8 @@ int niwqg_ipc_disable(niwqg_handle* h) {   // back to the NCCL all-to-all exchan
 
 int niwqg_sync(niwqg_handle* h) {
     CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->copy_out));
     return 0;
 }
 
@@ -1592,29 +1673,31 @@ int niwqg_status(niwqg_handle* h, double* out) {
         }
         return 0;
     }
+    // every result is copied into pinned host scratch in stream order (the next kernel may reuse sumsX): ONE sync
+    const int B = h->B;
+    double *p_ke = h->pin, *p_kw = p_ke + (size_t)B * SS_COUNT, *p_pw = p_kw + B, *p_cfl = p_pw + B;
     int r = ke_qg_family(h);
     if (r) return r;
-    CK(cudaMemcpyAsync(sx.data(), h->sumsX, (size_t)h->B * SS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int m = 0; m < h->B; ++m) out[m * 4 + 0] = 0.5 * sx[(size_t)m * SS_COUNT + SS_KE] / M2;
+    CK(cudaMemcpyAsync(p_ke, h->sumsX, (size_t)B * SS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     k_phi2_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->npts, h->part);
     CK(cudaGetLastError());
     FIN(1, h->sumsX);
-    CK(cudaMemcpyAsync(tmp.data(), h->sumsX, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int m = 0; m < h->B; ++m) out[m * 4 + 1] = 0.5 * tmp[m] / M;
+    CK(cudaMemcpyAsync(p_kw, h->sumsX, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     r = pe_niw_refresh(h, h->sumsX);
     if (r) return r;
-    CK(cudaMemcpyAsync(tmp.data(), h->sumsX, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int m = 0; m < h->B; ++m) out[m * 4 + 2] = 0.25 * tmp[m] / M / h->kappa2;
+    CK(cudaMemcpyAsync(p_pw, h->sumsX, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     k_cfl_max<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->uv, h->phi, h->npts, h->part);
     CK(cudaGetLastError());
     FIN(1, h->sumsX, 1);
-    CK(cudaMemcpyAsync(tmp.data(), h->sumsX, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p_cfl, h->sumsX, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->launches += 2;
-    for (int m = 0; m < h->B; ++m) out[m * 4 + 3] = tmp[m] * h->p.dt / h->dx;
+    for (int m = 0; m < B; ++m) {
+        out[m * 4 + 0] = 0.5 * p_ke[(size_t)m * SS_COUNT + SS_KE] / M2;
+        out[m * 4 + 1] = 0.5 * p_kw[m] / M;
+        out[m * 4 + 2] = 0.25 * p_pw[m] / M / h->kappa2;
+        out[m * 4 + 3] = p_cfl[m] * h->p.dt / h->dx;
+    }
     return 0;
 }
 
@@ -1670,6 +1753,12 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
         return 0;
     }
     // ---- kernel family: _calc_energy_conversion on the current state (stale phix/phiy for UnCoupled, F6)
+    // results land in pinned host scratch in stream order: one synchronisation for the whole tick
+    double* p_ss = h->pin;                                    // [B][SS_COUNT]
+    double* p_sd = p_ss + (size_t)B * 16;                     // [B][SD_COUNT]
+    double* p_sc = p_sd + (size_t)B * 16;                     // [B][NIWQG_S_COUNT]
+    double* p_s3 = p_sc + (size_t)B * NIWQG_S_COUNT;          // [B][3]
+    double* p_sg = p_s3 + (size_t)B * 3;                      // [B]
     const bool ybj = (h->flags & MF_YBJ) != 0;
     if (ybj || (h->flags & MF_SPEC_BUDGET)) {
         // lapphi = ifft(-wv2*phih) is recomputed by every _calc_energy_conversion (Kernel.py:685); during a step the
@@ -1685,9 +1774,9 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
     int r = ke_qg_family(h);      // spectral sums -> sumsX
     if (r) return r;
     // budget terms of the tick use Parseval sums from k_spec_sums: copy into the SE layout
-    CK(cudaMemcpyAsync(ss.data(), h->sumsX, (size_t)B * SS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(sd.data(), h->sumsD, (size_t)B * SD_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(sc.data(), h->scal, sc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p_ss, h->sumsX, (size_t)B * SS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p_sd, h->sumsD, (size_t)B * SD_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p_sc, h->scal, (size_t)B * NIWQG_S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     // conc_niw second pass (centred sums)
     k_qpsi_sum<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->qs, h->npts, h->part);
     CK(cudaGetLastError());
@@ -1695,22 +1784,22 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
     k_conc_sums<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->qs, h->npts, h->sumsD, h->sumsE, h->part);
     CK(cudaGetLastError());
     FIN(3, h->sumsE);
-    CK(cudaMemcpyAsync(s3.data(), h->sumsE, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p_s3, h->sumsE, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->launches += 3;
     // pe_niw: refreshes phix, phiy (Kernel.py:608-611) -- after the conversion terms, as in the registry order
     r = pe_niw_refresh(h, h->sumsE);
     if (r) return r;
-    CK(cudaMemcpyAsync(sg.data(), h->sumsE, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p_sg, h->sumsE, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const niwqg_params& p = h->p;
     for (int m = 0; m < B; ++m) {
         double* o = out + (size_t)m * NIWQG_S_COUNT;
-        const double* D = &sd[(size_t)m * SD_COUNT];
-        const double* S = &ss[(size_t)m * SS_COUNT];
+        const double* D = &p_sd[(size_t)m * SD_COUNT];
+        const double* S = &p_ss[(size_t)m * SS_COUNT];
         for (int k = 0; k < NIWQG_S_COUNT; ++k) o[k] = 0.0;
-        o[NIWQG_S_KE] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KE];
-        o[NIWQG_S_PW] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_PW];
-        o[NIWQG_S_KW] = sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KW];
+        o[NIWQG_S_KE] = p_sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KE];
+        o[NIWQG_S_PW] = p_sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_PW];
+        o[NIWQG_S_KW] = p_sc[(size_t)m * NIWQG_S_COUNT + NIWQG_S_KW];
         o[NIWQG_S_GAMMA1] = 0.5 * 0.5 * h->hslash * (D[SD_G1] / M) / p.f;
         o[NIWQG_S_GAMMA2] = 0.5 * h->hslash * (D[SD_G2] / M) / p.f;
         o[NIWQG_S_XI1] = (D[SD_X1] / M) / p.f;
@@ -1722,9 +1811,9 @@ int niwqg_diagnostics(niwqg_handle* h, double* out) {
         o[NIWQG_S_KE_NIW] = 0.5 * D[SD_PHI2] / M;
         o[NIWQG_S_CKE_NIW] = 0.5 * (ar * ar + ai * ai);
         o[NIWQG_S_IKE_NIW] = o[NIWQG_S_KE_NIW] - o[NIWQG_S_CKE_NIW];
-        const double grad2 = sg[m] / M;     // refreshed phix, phiy
+        const double grad2 = p_sg[m] / M;     // refreshed phix, phiy
         o[NIWQG_S_PE_NIW] = 0.25 * grad2 / h->kappa2;
-        const double* c3 = &s3[(size_t)m * 3];
+        const double* c3 = &p_s3[(size_t)m * 3];
         o[NIWQG_S_CONC] = (c3[0] / M) / sqrt(c3[1] / M) / sqrt(c3[2] / M);
         o[NIWQG_S_SKEW] = (D[SD_QP3] / M) / pow(D[SD_QP2] / M, 1.5);
         const double lap2m = D[SD_LAP2] / M, phi2m = D[SD_PHI2] / M;
@@ -1756,7 +1845,7 @@ size_t niwqg_field_bytes(const niwqg_handle* h, int field) {
     }
 }
 
-int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t bytes, int on_device) {
+static int get_field_impl(niwqg_handle* h, int field, int member, void* dst, size_t bytes, int on_device, bool async) {
     CK(cudaSetDevice(h->p.device));
     if (member < 0 || member >= h->B) { h->err = "get_field: bad member"; return -1; }
     if (bytes != niwqg_field_bytes(h, field)) { h->err = "get_field: size mismatch"; return -1; }
@@ -1833,16 +1922,30 @@ int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t by
     if (!src) { h->err = "get_field: field not defined for this model"; return -1; }
     switch (field) {   // physical fields leave in natural x order
         case NIWQG_F_Q: case NIWQG_F_QW: case NIWQG_F_QPSI: case NIWQG_F_U: case NIWQG_F_V: case NIWQG_F_C: case NIWQG_F_P:
-            r = download_phys<double>(h, (const double*)src, dst, h->npts, on_device, (double*)h->P2);
+            r = download_phys<double>(h, (const double*)src, dst, h->npts, on_device, (double*)h->P2, async);
             break;
         case NIWQG_F_PHI: case NIWQG_F_PHIX: case NIWQG_F_PHIY: case NIWQG_F_LAPPHI:
-            r = download_phys<cd>(h, (const cd*)src, dst, h->npts, on_device, h->P2);
+            r = download_phys<cd>(h, (const cd*)src, dst, h->npts, on_device, h->P2, async);
             break;
         default:
             CK(cudaMemcpyAsync(dst, src, bytes, kind, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
     }
-    if (r) return r;
-    CK(cudaStreamSynchronize(h->stream));
+    return r;
+}
+
+int niwqg_get_field(niwqg_handle* h, int field, int member, void* dst, size_t bytes, int on_device) {
+    return get_field_impl(h, field, member, dst, bytes, on_device, false);
+}
+
+int niwqg_get_field_async(niwqg_handle* h, int field, int member, void* dst, size_t bytes) {
+    return get_field_impl(h, field, member, dst, bytes, 0, true);
+}
+
+int niwqg_wait_transfers(niwqg_handle* h) {
+    CK(cudaSetDevice(h->p.device));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->copy_out));
     return 0;
 }
 

@@ -108,9 +108,10 @@ template <int N> static void run() {
         else CKE((launch_pass_g<N, true, true>(a, 1, st)));
     };
     // new path pieces
+    int row_bulk = 0;
     auto new_rows = [&](const cd* in, cd* out, double sc, int conj_out) {
         FftArgs a = base; a.in = in; a.out = out; a.tw = tw_half; a.nlines = 2 * N; a.pitch = Nh; a.mstride = (size_t)Nh * Nh;
-        a.g = Grid{Nh, dk, Nh, Nh / 2, 0, 0}; a.scale = sc; a.scale_im = conj_out ? -sc : sc;
+        a.g = Grid{Nh, dk, Nh, Nh / 2, 0, 0}; a.scale = sc; a.scale_im = conj_out ? -sc : sc; a.tma_in = row_bulk ? 2 : 0;
         CKE((launch_pass_g<Nh, false, true>(a, 1, st)));
     };
     auto new_colsub = [&](const cd* in, cd* out, bool dit) {
@@ -162,6 +163,16 @@ template <int N> static void run() {
     printf("      2-D transform: %.4f ms\n", o1 + o2);
     printf("   timing, split path:\n");
     float n1 = timeit("rows: 2N one-tile lines of N/2", [&] { new_rows(Ad, T1, 1.0, 0); });
+    row_bulk = 1;
+    timeit("rows, tiles fetched by cp.async.bulk (UBLKCP)", [&] { new_rows(Ad, T1, 1.0, 0); });
+    new_rows(Ad, T2, 1.0, 0);
+    row_bulk = 0;
+    new_rows(Ad, T1, 1.0, 0);
+    printf("      bulk-copy rows vs register-load rows: rel-L2 %.1e\n", err(T2, T1));
+    timeit("rows, bulk copy + no L2 prefetch", [&] { FftArgs a = base; a.in = Ad; a.out = T1; a.tw = tw_half; a.nlines = 2 * N; a.pitch = Nh;
+        a.mstride = (size_t)Nh * Nh; a.g = Grid{Nh, dk, Nh, Nh / 2, 0, 0}; a.pf_groups = 0; a.tma_in = 2; CKE((launch_pass_g<Nh, false, true>(a, 1, st))); });
+    timeit("rows, pf_groups = 0 (no L2 prefetch)", [&] { FftArgs a = base; a.in = Ad; a.out = T1; a.tw = tw_half; a.nlines = 2 * N; a.pitch = Nh;
+        a.mstride = (size_t)Nh * Nh; a.g = Grid{Nh, dk, Nh, Nh / 2, 0, 0}; a.pf_groups = 0; CKE((launch_pass_g<Nh, false, true>(a, 1, st))); });
     float n2 = timeit("k_fft_colsub2<DIT>", [&] { new_colsub(T1, OUT[0], true); });
     float n3 = timeit("k_split_p<DIT> in place", [&] { const int pro[1] = {PRO_NONE}; new_p(OUT[0], OUT, pro, 1, true, 0); });
     printf("      forward 2-D transform: %.4f ms\n", n1 + n2 + n3);
