@@ -65,11 +65,12 @@ def measured_peaks():
 
 
 def csrc_hash():
-    """Identity of the kernel sources a profile belongs to (profiles/traffic.json carries the hash it was captured on)."""
+    """Identity of the FFT kernel sources a traffic profile belongs to (profiles/traffic.json carries the hash it was
+    captured on): the files that define the 2-D transform launches."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "niwqg_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in ("common.cuh", "fft_core.cuh", "fft2d.cuh", "fft_split.cuh"):
         with open(os.path.join(d, f), "rb") as fh:
             h.update(f.encode()); h.update(fh.read())
     return h.hexdigest()[:16]
