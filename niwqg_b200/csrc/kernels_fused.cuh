@@ -37,7 +37,7 @@ struct FusedThread {
 };
 
 template <int N>
-__device__ __forceinline__ void fused_thread(int unit, int tid, const cd* __restrict__ twc, FusedThread& t) {
+__host__ __device__ __forceinline__ void fused_thread(int unit, int tid, const cd* __restrict__ twc, FusedThread& t) {
     using G = FusedGeom<N>;
     const int kk = unit / G::NB;
     int b = unit % G::NB, k;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void fused_thread(int unit, int tid, const cd* __rest
     t.kzero = (t.fam == 0);
     t.col = t.n + t.side * G::Nh;
 }
-__device__ __forceinline__ int fused_qp(const FusedThread& t, int q) { return t.kzero ? ((16 - q) & 15) : 15 - q; }
+__host__ __device__ __forceinline__ int fused_qp(const FusedThread& t, int q) { return t.kzero ? ((16 - q) & 15) : 15 - q; }
 
 __device__ __forceinline__ cd shfl16(cd v) {
     return make_double2(__shfl_xor_sync(0xffffffffu, v.x, 16), __shfl_xor_sync(0xffffffffu, v.y, 16));
@@ -85,6 +85,20 @@ __device__ __forceinline__ void fused_combine(const cd* __restrict__ T, const cd
     fftc::dft<16, 1>(v);
 #pragma unroll
     for (int p = 0; p < 16; ++p) u[fftc::outidx<16>(p)] = v[p];
+}
+
+// L2 prefetch of the column transforms the NEXT work unit of this CTA will combine (16 lines per thread): issued before
+// the long register-only phases of the current unit, so that the next fused_combine finds its operands in L2
+template <int N>
+__device__ __forceinline__ void fused_prefetch_next(const cd* __restrict__ T, const cd* __restrict__ twc, int unit, int tid) {
+    using G = FusedGeom<N>;
+    if (unit >= G::UNITS) return;
+    FusedThread t;
+    fused_thread<N>(unit, tid, twc, t);
+    if (tid & 7) return;                         // one request per 128 B line (8 consecutive columns)
+    constexpr int M = N / 16;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) prefetch_l2(&T[(size_t)(r * M + t.fam) * N + t.col]);
 }
 
 // inverse radix stage (decimation in frequency, see k_split_p<DIF>) of the 16 spectral values v[r] = s[fam + M r][col]:
@@ -126,6 +140,7 @@ struct FStageArgs {
     const cd* T;       // M-point column transforms (block layout) of the forward transform this kernel consumes
     cd* out[3];        // k_fstage_phi: radix-stage intermediates of phi, phix, phiy
     int nout;
+    int pf_next;       // L2 prefetch of the next unit's column transforms
     const cd* twc;
     double dk;
 };
@@ -200,6 +215,7 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) xs[q * 256 + tid] = u[q];      // parked: own value and the partner's come from here
         }
+        if (a.pf_next) fused_prefetch_next<N>(a.T, a.twc, unit + gridDim.x, tid);
         __syncthreads();
         const double k1 = a.dk * (double)sidx(t.col, N);
         const size_t i0 = (size_t)t.fam * N + t.col;
@@ -251,6 +267,7 @@ __global__ void __launch_bounds__(256, 2) k_fstage_phi(FStageArgs a) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) xs[q * 256 + tid] = u[q];      // parked (only this thread reads them back)
         }
+        if (a.pf_next) fused_prefetch_next<N>(a.T, a.twc, unit + gridDim.x, tid);
         const double k1 = a.dk * (double)sidx(t.col, N);
         const size_t i0 = (size_t)t.fam * N + t.col;
         double s[SE_COUNT];
@@ -308,6 +325,7 @@ struct FInvertArgs {
     InvertArgs i;
     const cd* T;       // M-point column transforms (block layout) of fft(|phi|^2 + i J): MF_WAVE_PV only
     cd *out_uv, *out_qs;
+    int pf_next;
     const cd* twc;
     double dk;
 };
@@ -333,6 +351,7 @@ __global__ void __launch_bounds__(256, 2) k_finvert(FInvertArgs a) {
             fused_combine<N>(a.T, a.twc, t, u);
 #pragma unroll
             for (int q = 0; q < 16; ++q) xs[q * 256 + tid] = u[q];
+            if (a.pf_next) fused_prefetch_next<N>(a.T, a.twc, unit + gridDim.x, tid);
             __syncthreads();
         }
         cd u[16];

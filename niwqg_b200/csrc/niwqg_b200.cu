@@ -120,9 +120,13 @@ struct niwqg_handle {
     void* stage_in = nullptr;                 // B * npts * 16 bytes
     void* stage_out[2] = {nullptr, nullptr};  // one member: real (npts * 8) / complex (npts * 16)
     double* pin = nullptr;                    // pinned host scratch for the scalars of diagnostics / status
+    int flag_barrier = 1;       // slab: peer-memory flags instead of the 1-element all-reduce between the two passes
+                                // (validated on 2 and 8 GPUs: 13.33 vs 13.47 ms/step at 8; NIWQG_SLAB_BARRIER=nccl switches back)
+    unsigned bar_epoch[NLANE] = {0, 0};
     int row_bulk = 1;           // split path: row tiles fetched by one bulk copy (cp.async.bulk; NIWQG_ROW_BULK=0: 16 LDG.128 per thread)
     int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
                                 // NIWQG_FUSED=0 runs the stage as launches of its own
+    int fused_pf = 0;           // fused kernels prefetch the next unit's operands into L2 (NIWQG_FUSED_PF=1)
     int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
     int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
     int tma = 1;                // column passes whose rows are narrower than a 128 B line fetch their tile by TMA
@@ -244,6 +248,29 @@ static int slab_all_to_all(niwqg_handle* h, const cd* send, cd* recv) {
 }
 
 static cudaError_t launch_col_natural(niwqg_handle* h, const FftArgs& a, int batch, int lane);
+static int slab_barrier(niwqg_handle* h, int lane, cudaStream_t st);
+
+// ---- cross-GPU barrier between the pushing pass of a slab transform and the pass that reads the receive buffer:
+// every rank raises a flag in every peer's memory once its pushes are behind it, and waits until all P flags in its own
+// memory have reached the transform's epoch.  Two 1-CTA launches on the lane's stream instead of a 1-element
+// ncclAllReduce (NIWQG_SLAB_BARRIER=nccl switches back).  The pushing kernel has completed when k_slab_signal runs (stream
+// order), so its peer stores are performed; the fence + system-scope store publish the flag after them.
+struct SlabFlags { unsigned* peer[8]; };
+__global__ void k_slab_signal(SlabFlags f, int nranks, int rank, unsigned epoch) {
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.peer[r] + rank), "r"(epoch) : "memory");
+}
+__global__ void k_slab_wait(const unsigned* flags, int nranks, unsigned epoch) {
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+        if (v < epoch) __nanosleep(200);
+    } while (v < epoch);
+}
 
 static void fft_common_args(niwqg_handle* h, FftArgs& a) {
     a.twc = h->twc;
@@ -389,7 +416,8 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
                                        chunk * sizeof(cd), cudaMemcpyDeviceToDevice, st));
                 }
             }
-            NK(g_nccl.AllReduce(h->bar[lane], h->bar[lane], 1, ncclDouble, ncclSum, h->lane_comm[lane], st));
+            int rb = slab_barrier(h, lane, st);
+            if (rb) return rb;
         }
         a.push = 0;
         a.in = h->Yp[lane][b]; a.out = final_out; a.pro = PRO_NONE; a.epi = epi; a.conj_in = 0;
@@ -479,7 +507,7 @@ static int slab_inv_push(niwqg_handle* h, const cd* in, int pro, int lane, int* 
     a.in = in; a.out = nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0; a.conj_out = 0;
     a.tw = h->tw_col; a.nlines = h->ncl; a.conj_in = 1;
     { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, 1, st)); }
-    { PROF_ON(PK_COMM, lane); NK(g_nccl.AllReduce(h->bar[lane], h->bar[lane], 1, ncclDouble, ncclSum, h->lane_comm[lane], st)); }
+    { PROF_ON(PK_COMM, lane); int rb = slab_barrier(h, lane, st); if (rb) return rb; }
     h->launches += 2;
     return 0;
 }
@@ -492,6 +520,20 @@ static int slab_inv_row(niwqg_handle* h, int lane, int b, cd* out, int pro) {
     a.deint_out = (h->deintC > 1);
     { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, 1, h->lane_stream[lane])); }
     h->launches++;
+    return 0;
+}
+
+static int slab_barrier(niwqg_handle* h, int lane, cudaStream_t st) {
+    if (!h->flag_barrier) {
+        NK(g_nccl.AllReduce(h->bar[lane], h->bar[lane], 1, ncclDouble, ncclSum, h->lane_comm[lane], st));
+        return 0;
+    }
+    SlabFlags f{};
+    for (int r = 0; r < h->nranks; ++r) f.peer[r] = (unsigned*)(h->peerY[lane][0][r] + h->npts);   // behind the receive buffer
+    const unsigned epoch = ++h->bar_epoch[lane];
+    k_slab_signal<<<1, 32, 0, st>>>(f, h->nranks, h->rank, epoch);
+    k_slab_wait<<<1, 32, 0, st>>>((const unsigned*)(h->Yp[lane][0] + h->npts), h->nranks, epoch);
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -746,7 +788,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         sa.y0q = h->qh[oq]; sa.y0p = h->phih[op]; sa.yq = h->qh[nq]; sa.yp = h->phih[np];
         sa.y1q = h->y1q; sa.y1p = h->y1p; sa.F0q = h->F0q; sa.F0p = h->F0p; sa.Fabq = h->Fabq; sa.Fabp = h->Fabp;
         sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
-        fa.twc = h->twc; fa.dk = h->dk;
+        fa.twc = h->twc; fa.dk = h->dk; fa.pf_next = h->fused_pf;
         fa.T = h->T[0];
         { PROF(PK_SPEC); CK((launch_fstage<N>(fa, false, grid, h->stream))); }
         fa.T = h->T[1];
@@ -779,7 +821,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         ia.i.filtr_sym = (h->p.use_filter || !h->p.dealias) ? 1 : 0;
         ia.i.ph = h->ph; ia.i.qs = h->qs; ia.i.W = h->T[0]; ia.i.qwh = (wave && st == 4) ? h->qwh : nullptr;
         ia.i.inv_jscale = 1.0 / h->jscale; ia.i.partials = h->part;
-        ia.T = h->T[0]; ia.out_uv = h->T[1]; ia.out_qs = h->T[2]; ia.twc = h->twc; ia.dk = h->dk;
+        ia.T = h->T[0]; ia.out_uv = h->T[1]; ia.out_qs = h->T[2]; ia.twc = h->twc; ia.dk = h->dk; ia.pf_next = h->fused_pf;
         { PROF(PK_SPEC); CK((launch_finvert<N>(ia, wave, grid, h->stream))); }
         h->launches++;
         FIN(SI_COUNT, h->sumsI, 0, grid);
@@ -1122,6 +1164,8 @@ static int create_impl(niwqg_handle* h) {
         h->split = e ? (atoi(e) != 0) : (N == 8192);
         if (const char* f = getenv("NIWQG_FUSED")) h->fused = atoi(f);
         if (const char* f = getenv("NIWQG_ROW_BULK")) h->row_bulk = atoi(f);
+        if (const char* f = getenv("NIWQG_FUSED_PF")) h->fused_pf = atoi(f);
+        if (const char* f = getenv("NIWQG_FUSED_GRID")) h->fused_grid = atoi(f);
         if (h->split) { h->deintM = N / 2; h->deintC = 2; }
     }
     h->g = Grid{N, 2.0 * M_PI / p.L, h->ncl, h->ncl / 2, h->rank, h->nranks > 1 ? 1 : 0};
@@ -1246,7 +1290,9 @@ static int create_impl(niwqg_handle* h) {
         DA(h->X, fsz); DA(h->Y, fsz);
         const int nl = getenv("NIWQG_ONE_LANE") ? 1 : niwqg_handle::NLANE;
         if (const char* e = getenv("NIWQG_GROUP_OCC_LIMIT")) h->group_occ_limit = atoi(e);
-        for (int l = 0; l < nl; ++l) { DA(h->Yp[l][0], fsz); DA(h->Yp[l][1], fsz); DA(h->bar[l], 64); DA(h->Xl[l], fsz); }
+        if (const char* e = getenv("NIWQG_SLAB_BARRIER")) h->flag_barrier = strcmp(e, "nccl") != 0;
+        // (+4 KB behind the first receive buffer of a lane: the barrier flags, mapped by the peers with the buffer)
+        for (int l = 0; l < nl; ++l) { DA(h->Yp[l][0], fsz + 4096); DA(h->Yp[l][1], fsz); DA(h->bar[l], 64); DA(h->Xl[l], fsz); }
         if (const char* e = getenv("NIWQG_SLAB_EXCHANGE")) h->exchange = (strcmp(e, "ce") == 0) ? 1 : 0;
         if (nl > 1) {
             CK(cudaStreamCreateWithFlags(&h->lane_stream[1], cudaStreamNonBlocking));

@@ -22,6 +22,20 @@ def test_fft_index_maps_on_cpu(tmp_path):
     assert "C=8" in out.stdout and "N= 8192" in out.stdout
 
 
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_fused_kernel_work_unit_geometry_on_cpu(tmp_path):
+    """kernels_fused.cuh: every spectral element is owned by exactly one thread of one work unit, lanes l / l+16 hold the
+    columns kx / kx+N/2, and the thread named as the holder of -K holds exactly (-ky, -kx) (tests/host/host_fused_map.cu)."""
+    import nvidia.nccl as n
+    inc = os.path.join(list(n.__path__)[0], "include")
+    exe = str(tmp_path / "host_fused_map")
+    subprocess.check_call([NVCC, "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", inc, "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "host_fused_map.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" 0 mapping errors, 0 elements not owned exactly once") == 3, out.stdout
+
+
 def test_library_exports_every_declared_symbol():
     import __graft_entry__ as ge
     ge.build()
