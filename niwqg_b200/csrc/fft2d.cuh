@@ -72,6 +72,10 @@ struct FftArgs {
                       // (position c*M + m holds x = C*m + c), so both cluster kernels touch contiguous memory
     int push;         // slab: the pass's stores go straight into the owners' receive buffers over NVLink (peer[])
     int nyl_shift;    // log2(rows per rank)
+    int panel;        // inverse slab transform, pushed exchange: the receive buffer is laid out in panels of 4 columns,
+                      // [source rank][panel][row residue mod C][row / C][4 columns] with C = panel = cluster size of the
+                      // pushing column pass, so that what one CTA pushes to one peer is contiguous (8 KB runs instead of
+                      // 64 B segments: 409 -> ~620 GB/s over NVLink, profiles/r02_nvlink_push_patterns_8gpu.txt); 0 = off
     cd* peer[8];      // receive buffer of every rank (peer[rank] = own), CUDA-IPC mapped
     size_t mstride;   // elements between ensemble members
     int tma_in;       // column pass, natural layout, one tile per line group: the tile is fetched by TMA (cp.async.bulk.tensor)
@@ -86,6 +90,14 @@ struct FftArgs {
 //   column pass: n-th row of local column `line`;  row pass: natural [line][n], or - on the exchange side of a slab
 //   transform - [owner(n)][line][lc(n)] (the layout ncclAlltoAll moves between the row slabs and the column slabs)
 // NAT: natural single-GPU layout - pitch N, no exchange maps, no pushes: all strides are compile-time constants
+// offset inside one source rank's chunk of the panel layout: local row yl (of nyl = 2^nyl_shift), local column lc
+__device__ __forceinline__ size_t panel_offset(const FftArgs& a, int yl, int lc) {
+    int cs = 0;
+    while ((1 << cs) < a.panel) ++cs;
+    const int rp = ((yl & (a.panel - 1)) << (a.nyl_shift - cs)) | (yl >> cs);      // residue-major row order
+    return ((((size_t)(lc >> 2)) << a.nyl_shift) + rp) * 4 + (lc & 3);
+}
+
 template <int N, bool COL, bool NAT>
 __device__ __forceinline__ size_t fft_index(const FftArgs& a, int xmap, int line, int n) {
     if (NAT) return COL ? (size_t)n * N + line : (size_t)line * N + n;
@@ -93,6 +105,7 @@ __device__ __forceinline__ size_t fft_index(const FftArgs& a, int xmap, int line
     if (!xmap) return (size_t)line * N + n;
     int r, lc;
     grid_owner(N, a.g.h, n, r, lc);
+    if (a.panel) return (size_t)r * a.xchunk + panel_offset(a, line, lc);
     return (size_t)r * a.xchunk + (size_t)line * a.g.ncl + lc;
 }
 // (ky, kx) of element n of line `line` on the spectral side (prologue wavenumbers)
@@ -130,7 +143,8 @@ __device__ __forceinline__ void fft_store(const FftArgs& a, size_t mbase, int li
         size_t off;
         if (COL) {               // inverse transform, column pass: row n belongs to rank n / nyl
             r = n >> a.nyl_shift;
-            off = (size_t)(n - (r << a.nyl_shift)) * a.g.ncl + line;
+            const int yl = n - (r << a.nyl_shift);
+            off = a.panel ? panel_offset(a, yl, line) : (size_t)yl * a.g.ncl + line;
         } else {                 // forward transform, row pass: column n belongs to owner(n)
             int lc;
             grid_owner(N, a.g.h, n, r, lc);

@@ -120,6 +120,8 @@ struct niwqg_handle {
     void* stage_in = nullptr;                 // B * npts * 16 bytes
     void* stage_out[2] = {nullptr, nullptr};  // one member: real (npts * 8) / complex (npts * 16)
     double* pin = nullptr;                    // pinned host scratch for the scalars of diagnostics / status
+    int slab_panel = 0;         // slab, pushed exchange of inverse transforms: panel receive layout (FftArgs::panel); = cluster
+                                // size of the column pass for N >= 1024 (NIWQG_SLAB_PANEL=0 keeps rows of ncl columns)
     int flag_barrier = 1;       // slab: peer-memory flags instead of the 1-element all-reduce between the two passes
                                 // (validated on 2 and 8 GPUs: 13.33 vs 13.47 ms/step at 8; NIWQG_SLAB_BARRIER=nccl switches back)
     unsigned bar_epoch[NLANE] = {0, 0};
@@ -395,6 +397,7 @@ static int fft2(niwqg_handle* h, const void* in, cd* out, bool inverse, int pro,
         int sh = 0;
         while ((1 << sh) < h->nyl) ++sh;
         a.nyl_shift = sh;
+        a.panel = (inverse && !ce) ? h->slab_panel : 0;      // both passes of the transform see the same receive layout
         a.in = in; a.out = ce ? (void*)h->Xl[lane] : nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0;
         a.conj_out = 0;
         if (!inverse) {
@@ -504,6 +507,7 @@ static int slab_inv_push(niwqg_handle* h, const cd* in, int pro, int lane, int* 
     int sh = 0;
     while ((1 << sh) < h->nyl) ++sh;
     a.nyl_shift = sh;
+    a.panel = h->slab_panel;
     a.in = in; a.out = nullptr; a.pro = pro; a.epi = EPI_NONE; a.scale = 1.0; a.scale_im = 1.0; a.conj_out = 0;
     a.tw = h->tw_col; a.nlines = h->ncl; a.conj_in = 1;
     { PROF_ON(PK_FFT_COL, lane); CK(launch_pass<true>(h->N, a, 1, st)); }
@@ -516,6 +520,10 @@ static int slab_inv_row(niwqg_handle* h, int lane, int b, cd* out, int pro) {
     fft_common_args(h, a);
     const double sc = 1.0 / ((double)h->N * (double)h->N);
     a.in = h->Yp[lane][b]; a.out = out; a.pro = pro; a.epi = EPI_NONE; a.conj_in = 0;
+    int sh = 0;
+    while ((1 << sh) < h->nyl) ++sh;
+    a.nyl_shift = sh;
+    a.panel = h->slab_panel;
     a.tw = h->tw_row; a.nlines = h->nyl; a.xmap_in = 1; a.conj_out = 1; a.scale = sc; a.scale_im = -sc;
     a.deint_out = (h->deintC > 1);
     { PROF_ON(PK_FFT_ROW, lane); CK(launch_pass<false>(h->N, a, 1, h->lane_stream[lane])); }
@@ -1291,6 +1299,8 @@ static int create_impl(niwqg_handle* h) {
         const int nl = getenv("NIWQG_ONE_LANE") ? 1 : niwqg_handle::NLANE;
         if (const char* e = getenv("NIWQG_GROUP_OCC_LIMIT")) h->group_occ_limit = atoi(e);
         if (const char* e = getenv("NIWQG_SLAB_BARRIER")) h->flag_barrier = strcmp(e, "nccl") != 0;
+        h->slab_panel = (N >= NIWQG_COL_M && h->nyl >= N / NIWQG_COL_M && h->ncl % 4 == 0) ? N / NIWQG_COL_M : 0;
+        if (const char* e = getenv("NIWQG_SLAB_PANEL")) if (!atoi(e)) h->slab_panel = 0;
         // (+4 KB behind the first receive buffer of a lane: the barrier flags, mapped by the peers with the buffer)
         for (int l = 0; l < nl; ++l) { DA(h->Yp[l][0], fsz + 4096); DA(h->Yp[l][1], fsz); DA(h->bar[l], 64); DA(h->Xl[l], fsz); }
         if (const char* e = getenv("NIWQG_SLAB_EXCHANGE")) h->exchange = (strcmp(e, "ce") == 0) ? 1 : 0;
