@@ -178,7 +178,10 @@ __device__ __forceinline__ void eq_prefetch(const cd* y0, const cd* y, const cd*
 }
 constexpr int FUSED_PD = 0;     // L2 prefetch distance in elements (0 = off: measured slower, 24.1 vs 22.2 ms of spectral kernels per step)
 // register pipeline depth of the element loop per stage: as deep as 128 registers allow
-template <int ST> struct FusedDepth { static constexpr int Q = ST <= 2 ? 4 : 3, PHI = ST <= 2 ? 4 : (ST == 3 ? 3 : 2), INV = 6; };
+#ifndef NIWQG_DEPTH_BOOST
+#define NIWQG_DEPTH_BOOST 0
+#endif
+template <int ST> struct FusedDepth { static constexpr int Q = (ST <= 2 ? 4 : 3) + NIWQG_DEPTH_BOOST, PHI = (ST <= 2 ? 4 : (ST == 3 ? 3 : 2)) + NIWQG_DEPTH_BOOST, INV = 6; };
 // etd_update (kernels_family.cuh) on preloaded operands; F0 / Fab come back as what the stage stores
 template <int ST>
 __device__ __forceinline__ cd eq_update(const EqIn& in, cd y0, cd Fn, cd& F0, cd& Fab) {
