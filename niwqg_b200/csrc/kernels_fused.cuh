@@ -141,6 +141,7 @@ struct FStageArgs {
     cd* out[3];        // k_fstage_phi: radix-stage intermediates of phi, phix, phiy
     int nout;
     int pf_next;       // L2 prefetch of the next unit's column transforms
+    int hsym;          // k_fstage_q: store the element at -K as the conjugate of the one at K (needs filtr(K) == filtr(-K))
     const cd* twc;
     double dk;
 };
@@ -224,6 +225,40 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
         const size_t i0 = (size_t)t.fam * N + t.col;
         constexpr int D = FusedDepth<ST>::Q;
         EqIn in[D];
+        if (a.hsym && !t.kzero) {
+            // q is real: every array of the q equation is Hermitian (y(-K) = conj y(K)) and so are its tables and the
+            // (symmetric) filter, hence the element at -K is the conjugate of the one at K.  -K of (this thread, q) is
+            // (partner thread, 15 - q): the thread updates its EVEN q and stores both elements, which halves the
+            // operand reads of the stage (y0 / F0 / Fab / y1 / tables: 28-60 B per grid point).
+            const int colp = (N - t.col) & (N - 1);
+#pragma unroll
+            for (int p = 0; p < D - 1; ++p) eq_load<ST, false>(in[p], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i0 + (size_t)(2 * p) * M * N);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+                const int q = 2 * qq;
+                const int ky = t.fam + M * q;
+                const size_t i1 = i0 + (size_t)q * M * N;
+                const size_t ip = (size_t)(N - ky) * N + colp;
+                if (qq + D - 1 < 8) eq_load<ST, false>(in[(qq + D - 1) % D], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i1 + (size_t)(2 * (D - 1)) * M * N);
+                const cd p1 = xs[q * 256 + tid], p2 = xs[(15 - q) * 256 + t.ptid];
+                const double l1 = a.dk * (double)sidx(ky, N);
+                const cd A = make_double2(0.5 * (p1.x + p2.x), 0.5 * (p1.y - p2.y));
+                const cd B = make_double2(0.5 * (p1.y + p2.y), -0.5 * (p1.x - p2.x));
+                const cd F1 = make_double2(k1 * A.y + l1 * B.y, -(k1 * A.x + l1 * B.x));
+                const EqIn& e = in[qq % D];
+                cd F0a, Faba;
+                const cd n1 = eq_update<ST>(e, e.y0, F1, F0a, Faba);
+                const cd n1c = make_double2(n1.x, -n1.y);
+                a.s.yq[i1] = n1; a.s.yq[ip] = n1c;
+                if (ST == 1) {
+                    a.s.F0q[i1] = F0a; a.s.F0q[ip] = make_double2(F0a.x, -F0a.y);
+                    a.s.y1q[i1] = n1; a.s.y1q[ip] = n1c;
+                }
+                if (ST == 2 || ST == 3) { a.s.Fabq[i1] = Faba; a.s.Fabq[ip] = make_double2(Faba.x, -Faba.y); }
+            }
+            __syncthreads();
+            continue;
+        }
 #pragma unroll
         for (int p = 0; p < D - 1; ++p) eq_load<ST, false>(in[p], a.s.y0q, a.s.yq, a.s.y1q, a.s.F0q, a.s.Fabq, a.s.tq, a.s.filtr, i0 + (size_t)p * M * N);
 #pragma unroll

@@ -128,6 +128,7 @@ struct niwqg_handle {
     int row_bulk = 1;           // split path: row tiles fetched by one bulk copy (cp.async.bulk; NIWQG_ROW_BULK=0: 16 LDG.128 per thread)
     int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
                                 // NIWQG_FUSED=0 runs the stage as launches of its own
+    int fused_hsym = 1;         // k_fstage_q updates one element of every (K, -K) pair and stores both (NIWQG_FUSED_HSYM=0: every element)
     int fused_pf = 0;           // fused kernels prefetch the next unit's operands into L2 (NIWQG_FUSED_PF=1)
     int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
     int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
@@ -797,6 +798,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         sa.y1q = h->y1q; sa.y1p = h->y1p; sa.F0q = h->F0q; sa.F0p = h->F0p; sa.Fabq = h->Fabq; sa.Fabp = h->Fabp;
         sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
         fa.twc = h->twc; fa.dk = h->dk; fa.pf_next = h->fused_pf;
+        fa.hsym = (h->fused_hsym && (h->p.use_filter || !h->p.dealias)) ? 1 : 0;
         fa.T = h->T[0];
         { PROF(PK_SPEC); CK((launch_fstage<N>(fa, false, grid, h->stream))); }
         fa.T = h->T[1];
@@ -1173,6 +1175,7 @@ static int create_impl(niwqg_handle* h) {
         if (const char* f = getenv("NIWQG_FUSED")) h->fused = atoi(f);
         if (const char* f = getenv("NIWQG_ROW_BULK")) h->row_bulk = atoi(f);
         if (const char* f = getenv("NIWQG_FUSED_PF")) h->fused_pf = atoi(f);
+        if (const char* f = getenv("NIWQG_FUSED_HSYM")) h->fused_hsym = atoi(f);
         if (const char* f = getenv("NIWQG_FUSED_GRID")) h->fused_grid = atoi(f);
         if (h->split) { h->deintM = N / 2; h->deintC = 2; }
     }
