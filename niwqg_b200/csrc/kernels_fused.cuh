@@ -157,7 +157,7 @@ __device__ __forceinline__ void eq_load(EqIn& in, const cd* __restrict__ y0, con
                                         const cd* __restrict__ F0, const cd* Fab, const TableSet& t,
                                         const double* __restrict__ filtr, size_t i) {
     in.y0 = __ldg(&y0[i]);
-    if (PHI && ST >= 2) in.cur = y[i];
+    if (PHI && ST >= 2) in.cur = (ST == 2) ? __ldg(&y1[i]) : y[i];     // stage 2: the stage-1 result lives in y1
     if (ST >= 3) { in.F0 = __ldg(&F0[i]); in.Fab = (ST == 4) ? __ldg(&Fab[i]) : Fab[i]; }
     if (ST == 3) in.y1 = __ldg(&y1[i]);
     if (ST <= 3) { in.c0 = __ldg(&t.E2[i]); in.c1 = __ldg(&t.Q[i]); }
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
                 a.s.yq[i1] = n1; a.s.yq[ip] = n1c;
                 if (ST == 1) {
                     a.s.F0q[i1] = F0a; a.s.F0q[ip] = make_double2(F0a.x, -F0a.y);
-                    a.s.y1q[i1] = n1; a.s.y1q[ip] = n1c;
+                    if (a.s.y1q != a.s.yq) { a.s.y1q[i1] = n1; a.s.y1q[ip] = n1c; }
                 }
                 if (ST == 2 || ST == 3) { a.s.Fabq[i1] = Faba; a.s.Fabq[ip] = make_double2(Faba.x, -Faba.y); }
             }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
             cd F0a, Faba;
             const cd n1 = eq_update<ST>(e, e.y0, F1, F0a, Faba);
             a.s.yq[i1] = n1;
-            if (ST == 1) { a.s.F0q[i1] = F0a; a.s.y1q[i1] = n1; }
+            if (ST == 1) { a.s.F0q[i1] = F0a; if (a.s.y1q != a.s.yq) a.s.y1q[i1] = n1; }
             if (ST == 2 || ST == 3) a.s.Fabq[i1] = Faba;
         }
         __syncthreads();
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256, 2) k_fstage_phi(FStageArgs a) {
             cd F0a, Faba;
             const cd n1 = eq_update<ST>(e, e.y0, F1, F0a, Faba);
             a.s.yp[i1] = n1;
-            if (ST == 1) { a.s.F0p[i1] = F0a; a.s.y1p[i1] = n1; }
+            if (ST == 1) { a.s.F0p[i1] = F0a; if (a.s.y1p != a.s.yp) a.s.y1p[i1] = n1; }
             if (ST == 2 || ST == 3) a.s.Fabp[i1] = Faba;
         }
 #pragma unroll

@@ -796,6 +796,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         sa.P1 = h->P1; sa.P2 = h->P2;
         sa.y0q = h->qh[oq]; sa.y0p = h->phih[op]; sa.yq = h->qh[nq]; sa.yp = h->phih[np];
         sa.y1q = h->y1q; sa.y1p = h->y1p; sa.F0q = h->F0q; sa.F0p = h->F0p; sa.Fabq = h->Fabq; sa.Fabp = h->Fabp;
+        if (st == 1) { sa.yq = h->y1q; sa.yp = h->y1p; }     // the stage-1 state is written once, as y1 (read again at stage 3)
         sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
         fa.twc = h->twc; fa.dk = h->dk; fa.pf_next = h->fused_pf;
         fa.hsym = (h->fused_hsym && (h->p.use_filter || !h->p.dealias)) ? 1 : 0;
@@ -827,7 +828,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         }
         // _invert(); _calc_rel_vorticity(); u, v
         FInvertArgs ia{};
-        ia.i.g = h->g; ia.i.flags = h->flags; ia.i.f = h->p.f; ia.i.qh = h->qh[h->cq]; ia.i.filtr = h->filtr;
+        ia.i.g = h->g; ia.i.flags = h->flags; ia.i.f = h->p.f; ia.i.qh = (st == 1) ? h->y1q : h->qh[h->cq]; ia.i.filtr = h->filtr;
         ia.i.filtr_sym = (h->p.use_filter || !h->p.dealias) ? 1 : 0;
         ia.i.ph = h->ph; ia.i.qs = h->qs; ia.i.W = h->T[0]; ia.i.qwh = (wave && st == 4) ? h->qwh : nullptr;
         ia.i.inv_jscale = 1.0 / h->jscale; ia.i.partials = h->part;
