@@ -382,6 +382,7 @@ struct StageArgs {
     int do_q;         // 0 for YBJ (and for the phi half of a split stage)
     int do_phi;       // 0 for the q half of a split stage
     int sums_here;    // this launch evaluates the stage's spectral budget sums (exactly one launch per stage does)
+    int hsym;         // q equation: store the element at -K as the conjugate of the one at K (needs filtr(K) == filtr(-K))
     const cd *P1, *P2;
     const cd *y0q, *y0p;      // state at the start of the step
     cd *yq, *yp;              // current stage state (stage 1: output buffers distinct from y0)
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
         const bool mode00 = (ky == 0 && kx == 0);
         const size_t i1 = mb + t1, i2 = mb + t2;
         const bool self = (t1 == t2);
-        const double fl1 = a.filtr[t1], fl2 = a.filtr[t2];
+        const double fl1 = a.filtr[t1], fl2 = a.hsym ? fl1 : a.filtr[t2];   // hsym implies filtr(K) == filtr(-K)
         const bool specb = (a.flags & MF_SPEC_BUDGET) != 0;
         if (a.sums_here && (specb || (a.flags & MF_HAS_LAP2))) {   // |phih|^2 moments on the pre-update phih (Kernel.py:629-652)
             const cd c1 = (st == 1) ? a.y0p[i1] : a.yp[i1], c2 = (st == 1) ? a.y0p[i2] : a.yp[i2];
@@ -487,17 +488,28 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_spec_stage(StageArgs a) {
             cd F1 = make_double2(k1 * A.y + l1 * B.y, -(k1 * A.x + l1 * B.x));
             cd F2 = make_double2(-(k2 * A.y + l2 * B.y), -(k2 * A.x + l2 * B.x));
             if (mode00) { F1 = make_double2(0.0, 0.0); F2 = F1; }
-            cd F0a, F0b, Faba, Fabb, y1a, y1b;
-            if (st >= 3) { F0a = a.F0q[i1]; F0b = a.F0q[i2]; }
-            if (st >= 3) { Faba = a.Fabq[i1]; Fabb = a.Fabq[i2]; }
-            if (st == 3) { y1a = a.y1q[i1]; y1b = a.y1q[i2]; }
-            const cd b1 = a.y0q[i1], b2 = a.y0q[i2];      // the ep_psi sums of this state: k_spec_invert
+            // q is real: every array of the q equation, its tables and the (symmetric) filter are Hermitian, so with
+            // a.hsym the element at -K is stored as the conjugate of the one at K and none of its operands are read
+            // (not on the Nyquist lines: numpy's signed wavenumber there is -N/2 for K and for -K alike, so the reference's
+            // Jacobian and tables are not conjugate-symmetric on them)
+            const bool hs = a.hsym && !self && kx != H && ky != H;
+            cd F0a, F0b, Faba, Fabb, y1a, y1b, b2;
+            if (st >= 3) { F0a = a.F0q[i1]; if (!hs) F0b = a.F0q[i2]; }
+            if (st >= 3) { Faba = a.Fabq[i1]; if (!hs) Fabb = a.Fabq[i2]; }
+            if (st == 3) { y1a = a.y1q[i1]; if (!hs) y1b = a.y1q[i2]; }
+            const cd b1 = a.y0q[i1];                       // the ep_psi sums of this state: k_spec_invert
+            if (!hs) b2 = a.y0q[i2];
             const cd n1 = etd_update(st, b1, y1a, F1, F0a, Faba, a.tq, t1, fl1);
             a.yq[i1] = n1;
             if (st == 1) { a.F0q[i1] = F0a; a.y1q[i1] = n1; }
             if (st == 2 || st == 3) a.Fabq[i1] = Faba;
             if (!self) {
-                const cd n2 = etd_update(st, b2, y1b, F2, F0b, Fabb, a.tq, t2, fl2);
+                cd n2;
+                if (hs) {
+                    n2 = make_double2(n1.x, -n1.y);
+                    F0b = make_double2(F0a.x, -F0a.y);
+                    Fabb = make_double2(Faba.x, -Faba.y);
+                } else n2 = etd_update(st, b2, y1b, F2, F0b, Fabb, a.tq, t2, fl2);
                 a.yq[i2] = n2;
                 if (st == 1) { a.F0q[i2] = F0b; a.y1q[i2] = n2; }
                 if (st == 2 || st == 3) a.Fabq[i2] = Fabb;

@@ -141,7 +141,6 @@ struct FStageArgs {
     cd* out[3];        // k_fstage_phi: radix-stage intermediates of phi, phix, phiy
     int nout;
     int pf_next;       // L2 prefetch of the next unit's column transforms
-    int hsym;          // k_fstage_q: store the element at -K as the conjugate of the one at K (needs filtr(K) == filtr(-K))
     const cd* twc;
     double dk;
 };
@@ -225,7 +224,11 @@ __global__ void __launch_bounds__(256, 2) k_fstage_q(FStageArgs a) {
         const size_t i0 = (size_t)t.fam * N + t.col;
         constexpr int D = FusedDepth<ST>::Q;
         EqIn in[D];
-        if (a.hsym && !t.kzero) {
+        // (units that hold the Nyquist column N/2 take the element-by-element path: the signed wavenumber of that
+        // column is -N/2 for K and -K alike, so the reference is not conjugate-symmetric on it; same for row family 0)
+        const int ub = unit % G::NB;
+        const bool nyq = (ub == 0) || (unit < G::NB && ub == G::NB / 2);
+        if (a.s.hsym && !t.kzero && !nyq) {
             // q is real: every array of the q equation is Hermitian (y(-K) = conj y(K)) and so are its tables and the
             // (symmetric) filter, hence the element at -K is the conjugate of the one at K.  -K of (this thread, q) is
             // (partner thread, 15 - q): the thread updates its EVEN q and stores both elements, which halves the

@@ -128,7 +128,7 @@ struct niwqg_handle {
     int row_bulk = 1;           // split path: row tiles fetched by one bulk copy (cp.async.bulk; NIWQG_ROW_BULK=0: 16 LDG.128 per thread)
     int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
                                 // NIWQG_FUSED=0 runs the stage as launches of its own
-    int fused_hsym = 1;         // k_fstage_q updates one element of every (K, -K) pair and stores both (NIWQG_FUSED_HSYM=0: every element)
+    int hsym = 1;               // q-equation stage kernels update one element of every (K, -K) pair and store both (NIWQG_HSYM=0: every element)
     int fused_pf = 0;           // fused kernels prefetch the next unit's operands into L2 (NIWQG_FUSED_PF=1)
     int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
     int split_stage = 1;        // k_spec_stage as two lighter launches (q equation / phi equation): NIWQG_SPLIT_STAGE=0 fuses
@@ -799,7 +799,7 @@ static int step_family_fused_n(niwqg_handle* h) {
         if (st == 1) { sa.yq = h->y1q; sa.yp = h->y1p; }     // the stage-1 state is written once, as y1 (read again at stage 3)
         sa.ph = h->ph; sa.tq = h->tq; sa.tp = h->tp; sa.filtr = h->filtr; sa.sumsD = h->sumsD; sa.partials = h->part;
         fa.twc = h->twc; fa.dk = h->dk; fa.pf_next = h->fused_pf;
-        fa.hsym = (h->fused_hsym && (h->p.use_filter || !h->p.dealias)) ? 1 : 0;
+        sa.hsym = (h->hsym && (h->p.use_filter || !h->p.dealias)) ? 1 : 0;
         fa.T = h->T[0];
         { PROF(PK_SPEC); CK((launch_fstage<N>(fa, false, grid, h->stream))); }
         fa.T = h->T[1];
@@ -869,6 +869,7 @@ static int step_family(niwqg_handle* h) {
         StageArgs sa{};
         sa.g = h->g;
         sa.stage = st; sa.flags = h->flags; sa.do_q = ybj ? 0 : 1; sa.do_phi = 1;
+        sa.hsym = (h->hsym && (h->p.use_filter || !h->p.dealias)) ? 1 : 0;
         sa.P1 = h->P1; sa.P2 = h->P2;
         sa.y0q = h->qh[oq]; sa.y0p = h->phih[op]; sa.yq = h->qh[nq]; sa.yp = h->phih[np];
         sa.y1q = h->y1q; sa.y1p = h->y1p; sa.F0q = h->F0q; sa.F0p = h->F0p; sa.Fabq = h->Fabq; sa.Fabp = h->Fabp;
@@ -1149,6 +1150,7 @@ static int create_impl(niwqg_handle* h) {
     if (const char* e = getenv("NIWQG_TMA")) h->tma = atoi(e);
     if (const char* e = getenv("NIWQG_SPLIT_STAGE")) h->split_stage = atoi(e);
     if (const char* e = getenv("NIWQG_COL3")) h->col3 = atoi(e);
+    if (const char* e = getenv("NIWQG_HSYM")) h->hsym = atoi(e);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -1176,7 +1178,6 @@ static int create_impl(niwqg_handle* h) {
         if (const char* f = getenv("NIWQG_FUSED")) h->fused = atoi(f);
         if (const char* f = getenv("NIWQG_ROW_BULK")) h->row_bulk = atoi(f);
         if (const char* f = getenv("NIWQG_FUSED_PF")) h->fused_pf = atoi(f);
-        if (const char* f = getenv("NIWQG_FUSED_HSYM")) h->fused_hsym = atoi(f);
         if (const char* f = getenv("NIWQG_FUSED_GRID")) h->fused_grid = atoi(f);
         if (h->split) { h->deintM = N / 2; h->deintC = 2; }
     }
