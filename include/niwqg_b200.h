@@ -100,12 +100,21 @@ int niwqg_destroy(niwqg_handle* h);
 const char* niwqg_last_error(const niwqg_handle* h);   /* h may be NULL: last create error */
 
 /* set_q (niwqg/Kernel.py:520-535, niwqg/QGModel.py:507-520): q is batch*N*N doubles on the
- * host (on_device=0) or device (1).  Inverts with whatever phi is current (F5). */
+ * host (on_device=0) or device (1).  Inverts with whatever phi is current (F5).  q == NULL: use the array queued by
+ * niwqg_stage_q. */
 int niwqg_set_q(niwqg_handle* h, const double* q, int on_device);
-/* set_phi (niwqg/Kernel.py:538-551): phi is batch*N*N interleaved complex doubles. */
+/* set_phi (niwqg/Kernel.py:538-551): phi is batch*N*N interleaved complex doubles (NULL: the array queued by
+ * niwqg_stage_phi). */
 int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device);
 /* set_c (niwqg/QGModel.py:522-534) */
 int niwqg_set_c(niwqg_handle* h, const double* c, int on_device);
+/* Input pipeline for a caller that seeds every step from host arrays (bench.py's end-to-end leg): queue the upload of
+ * the NEXT niwqg_set_q / niwqg_set_phi input from a (pinned) host array on the handle's copy stream and return at once,
+ * so the copy runs while the device is still stepping.  A following niwqg_set_q(h, NULL, 0) / niwqg_set_phi(h, NULL, 0)
+ * seeds the model from the staged array exactly as if it had been passed directly.  The host array must stay unchanged
+ * until that call returns.  Same layout and size as the set_* argument (this rank's rows in a slab run). */
+int niwqg_stage_q(niwqg_handle* h, const double* q);
+int niwqg_stage_phi(niwqg_handle* h, const double* phi);
 
 /* Initial conditions generated on the device (niwqg/InitialConditions.py), then seeded exactly like set_q / set_phi:
  * no whole-grid host array is involved (at 8192^2 the reference generators need several 1 GiB arrays, a Python loop

@@ -247,12 +247,23 @@ class Kernel(object):
             self.t += self.dt
 
     # ---------------------------------------------------------------- seeding
-    def set_q(self, q):
+    def set_q(self, q=None):
         """niwqg/Kernel.py:520-535 (inverts with the current phi, F5).  ``self.ke = Ke`` of the reference is served on
         first read (property below): reading it here would make the host wait for the inversion, which otherwise runs
-        on the device while the caller already uploads phi."""
+        on the device while the caller already uploads phi.  ``q=None`` (extension): seed from the array queued with
+        ``stage_inputs``."""
         self._h.set_q(q)
         self._ke = None
+
+    def stage_inputs(self, q=None, phi=None):
+        """Extension (no reference counterpart): start the host-to-device copy of the NEXT ``set_q()`` / ``set_phi()``
+        arguments now, on the copy stream, and return at once - the copy then overlaps the steps in between.  The
+        arrays (pinned host memory for a truly asynchronous copy) must stay unchanged until ``set_q()`` / ``set_phi()``
+        - called without an argument - have consumed them."""
+        if q is not None:
+            self._h.stage_q(q)
+        if phi is not None:
+            self._h.stage_phi(phi)
 
     @property
     def ke(self):
@@ -264,8 +275,8 @@ class Kernel(object):
     def ke(self, value):
         self._ke = value
 
-    def set_phi(self, phi):
-        """niwqg/Kernel.py:538-551 (does not re-invert, F5)."""
+    def set_phi(self, phi=None):
+        """niwqg/Kernel.py:538-551 (does not re-invert, F5).  ``phi=None``: the array queued with ``stage_inputs``."""
         self._h.set_phi(phi)
 
     # ---------------------------------------------------------------- status

@@ -150,9 +150,14 @@ class Model(object):
             self.tc += 1
             self.t += self.dt
 
-    def set_q(self, q):
-        """niwqg/QGModel.py:507-520."""
+    def set_q(self, q=None):
+        """niwqg/QGModel.py:507-520.  ``q=None`` (extension): the array queued with ``stage_inputs``."""
         self._h.set_q(q)
+
+    def stage_inputs(self, q=None):
+        """Extension: start the upload of the next ``set_q()`` argument now (see Kernel.stage_inputs)."""
+        if q is not None:
+            self._h.stage_q(q)
 
     def set_c(self, c):
         """niwqg/QGModel.py:522-534."""

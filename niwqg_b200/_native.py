@@ -39,7 +39,7 @@ EXPORTS = ["niwqg_create", "niwqg_destroy", "niwqg_last_error", "niwqg_set_q", "
            "niwqg_step", "niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars", "niwqg_get_field",
            "niwqg_field_bytes", "niwqg_fft2", "niwqg_jacobian", "niwqg_sync", "niwqg_time_steps",
            "niwqg_launch_count", "niwqg_stream", "niwqg_profile", "niwqg_nccl_unique_id", "niwqg_ic",
-           "niwqg_get_field_async", "niwqg_wait_transfers",
+           "niwqg_get_field_async", "niwqg_wait_transfers", "niwqg_stage_q", "niwqg_stage_phi",
            "niwqg_ipc_export", "niwqg_ipc_import", "niwqg_ipc_disable"]
 
 
@@ -72,6 +72,8 @@ def load():
     lib.niwqg_last_error.restype = C.c_char_p
     for n in ("niwqg_set_q", "niwqg_set_phi", "niwqg_set_c"):
         getattr(lib, n).argtypes = [vp, vp, ip]
+    for n in ("niwqg_stage_q", "niwqg_stage_phi"):
+        getattr(lib, n).argtypes = [vp, vp]
     lib.niwqg_ic.argtypes = [vp, ip, vp, ip, vp]
     lib.niwqg_step.argtypes = [vp, ip]
     for n in ("niwqg_diagnostics", "niwqg_status", "niwqg_get_scalars"):
@@ -169,6 +171,7 @@ class Handle(object):
             else:
                 setattr(p, k, v)
         self.params = p
+        self._staged = {}
         self.h = C.c_void_p()
         rc = self.lib.niwqg_create(C.byref(p), C.byref(self.h))
         if rc != 0:
@@ -227,13 +230,34 @@ class Handle(object):
 
     # The library returns from set_* once the host array has been copied (the caller may reuse it); the inversion and
     # transforms that follow stay queued on the handle's stream, and every later call is ordered behind them.
-    def set_q(self, q):
+    # q / phi None: seed from the array queued by stage_q / stage_phi (uploaded while the device was busy).
+    def set_q(self, q=None):
+        if q is None:
+            self._ck(self.lib.niwqg_set_q(self.h, None, 0))
+            self._staged.pop("q", None)
+            return
         a = self._host(q, np.float64)
         self._ck(self.lib.niwqg_set_q(self.h, a.ctypes.data, 0))
 
-    def set_phi(self, phi):
+    def set_phi(self, phi=None):
+        if phi is None:
+            self._ck(self.lib.niwqg_set_phi(self.h, None, 0))
+            self._staged.pop("phi", None)
+            return
         a = self._host(phi, np.complex128)
         self._ck(self.lib.niwqg_set_phi(self.h, a.ctypes.data, 0))
+
+    def stage_q(self, q):
+        """Queue the upload of the next set_q() input (niwqg_stage_q): returns at once; the array is kept alive here
+        and must not be written to until set_q() has returned."""
+        a = self._host(q, np.float64)
+        self._staged["q"] = a
+        self._ck(self.lib.niwqg_stage_q(self.h, a.ctypes.data))
+
+    def stage_phi(self, phi):
+        a = self._host(phi, np.complex128)
+        self._staged["phi"] = a
+        self._ck(self.lib.niwqg_stage_phi(self.h, a.ctypes.data))
 
     def set_c(self, c):
         a = self._host(c, np.float64)

@@ -118,6 +118,10 @@ struct niwqg_handle {
     cudaEvent_t ev_up_done = nullptr, ev_up_free = nullptr, ev_dn_ready = nullptr, ev_dn_done[2] = {nullptr, nullptr};
     bool up_free_rec = false, dn_done_rec[2] = {false, false};
     void* stage_in = nullptr;                 // B * npts * 16 bytes
+    // niwqg_stage_q / niwqg_stage_phi: the next set_* input, uploaded ahead of time ([0] q, [1] phi)
+    void* pre_buf[2] = {nullptr, nullptr};
+    cudaEvent_t pre_done[2] = {nullptr, nullptr}, pre_free[2] = {nullptr, nullptr};
+    bool pre_staged[2] = {false, false}, pre_free_rec[2] = {false, false};
     void* stage_out[2] = {nullptr, nullptr};  // one member: real (npts * 8) / complex (npts * 16)
     double* pin = nullptr;                    // pinned host scratch for the scalars of diagnostics / status
     int slab_panel = 0;         // slab, pushed exchange of inverse transforms: panel receive layout (FftArgs::panel); = cluster
@@ -1070,6 +1074,38 @@ static int upload_phys(niwqg_handle* h, const void* src, T* dst, size_t nelem, i
     CK(cudaEventSynchronize(h->ev_up_done));    // the caller may reuse its buffer when we return
     return 0;
 }
+// niwqg_stage_*: host -> pre_buf[w] on the copy stream, no wait
+static int stage_upload(niwqg_handle* h, int w, const void* src, size_t bytes) {
+    if (!src) { h->err = "stage: null host array"; return -1; }
+    if (!h->pre_buf[w]) {
+        CK(cudaMalloc(&h->pre_buf[w], bytes));
+        CK(cudaEventCreateWithFlags(&h->pre_done[w], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->pre_free[w], cudaEventDisableTiming));
+    }
+    if (h->pre_free_rec[w]) CK(cudaStreamWaitEvent(h->copy_stream, h->pre_free[w], 0));   // the previous consumer has read it
+    CK(cudaMemcpyAsync(h->pre_buf[w], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->pre_done[w], h->copy_stream));
+    h->pre_staged[w] = true;
+    return 0;
+}
+// set_*(NULL): pre_buf[w] -> field (device layout) on the main stream
+template <typename T>
+static int upload_staged(niwqg_handle* h, int w, T* dst, size_t nelem) {
+    if (!h->pre_staged[w]) { h->err = "set_q / set_phi without an array: nothing was staged (niwqg_stage_q / niwqg_stage_phi)"; return -1; }
+    CK(cudaStreamWaitEvent(h->stream, h->pre_done[w], 0));
+    if (h->deintC > 1) {
+        k_deint<T><<<NIWQG_PW_BLOCKS, NIWQG_PW_THREADS, 0, h->stream>>>((const T*)h->pre_buf[w], dst, nelem, h->N, h->deintM, h->deintC, 1);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
+        CK(cudaMemcpyAsync(dst, h->pre_buf[w], nelem * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(cudaEventRecord(h->pre_free[w], h->stream));
+    h->pre_free_rec[w] = true;
+    h->pre_staged[w] = false;
+    CK(cudaEventSynchronize(h->pre_done[w]));   // the caller may reuse its buffer when we return
+    return 0;
+}
 // field (device layout) -> caller.  async: returns once the copy is queued (niwqg_wait_transfers completes it)
 template <typename T>
 static int download_phys(niwqg_handle* h, const T* src, void* dst, size_t nelem, int on_device, T* stage, bool async = false) {
@@ -1133,6 +1169,11 @@ int niwqg_destroy(niwqg_handle* h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->copy_out) { cudaStreamSynchronize(h->copy_out); cudaStreamDestroy(h->copy_out); }
     for (cudaEvent_t e : {h->ev_up_done, h->ev_up_free, h->ev_dn_ready, h->ev_dn_done[0], h->ev_dn_done[1]}) if (e) cudaEventDestroy(e);
+    for (int w = 0; w < 2; ++w) {
+        if (h->pre_buf[w]) cudaFree(h->pre_buf[w]);
+        if (h->pre_done[w]) cudaEventDestroy(h->pre_done[w]);
+        if (h->pre_free[w]) cudaEventDestroy(h->pre_free[w]);
+    }
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1520,8 +1561,13 @@ __global__ void k_phi2_sum(const cd* __restrict__ phi, size_t npts, double* part
 int niwqg_set_q(niwqg_handle* h, const double* q, int on_device) {
     CK(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->B * h->npts;
-    { int r0 = upload_phys<double>(h, q, h->rscratch, n, on_device); if (r0) return r0; }
+    { int r0 = q ? upload_phys<double>(h, q, h->rscratch, n, on_device) : upload_staged<double>(h, 0, h->rscratch, n); if (r0) return r0; }
     return seed_q(h);
+}
+
+int niwqg_stage_q(niwqg_handle* h, const double* q) {
+    CK(cudaSetDevice(h->p.device));
+    return stage_upload(h, 0, q, (size_t)h->B * h->npts * sizeof(double));
 }
 
 // set_phi once the physical phi sits in h->phi in the device layout
@@ -1551,8 +1597,14 @@ int niwqg_set_phi(niwqg_handle* h, const double* phi, int on_device) {
     if (h->qg) { h->err = "set_phi: QGModel has no wave field"; return -1; }
     CK(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->B * h->npts;
-    { int r0 = upload_phys<cd>(h, phi, h->phi, n, on_device); if (r0) return r0; }
+    { int r0 = phi ? upload_phys<cd>(h, phi, h->phi, n, on_device) : upload_staged<cd>(h, 1, h->phi, n); if (r0) return r0; }
     return seed_phi(h);
+}
+
+int niwqg_stage_phi(niwqg_handle* h, const double* phi) {
+    if (h->qg) { h->err = "stage_phi: QGModel has no wave field"; return -1; }
+    CK(cudaSetDevice(h->p.device));
+    return stage_upload(h, 1, phi, (size_t)h->B * h->npts * sizeof(cd));
 }
 
 int niwqg_ic(niwqg_handle* h, int kind, const double* prm, int nprm, const double* rand01) {

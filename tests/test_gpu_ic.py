@@ -96,3 +96,31 @@ def test_8192_model_and_device_ic_in_seconds():
     assert abs(m.Ke - m2.Ke) <= 1e-12 * abs(m2.Ke) and abs(m.Kw - m2.Kw) <= 1e-12 * abs(m2.Kw)
     assert np.max(np.abs(m.q[4000:4200] - q[4000:4200])) <= 1e-13 * np.abs(q).max()
     assert dt < 5.0, dt
+
+
+@pytest.mark.parametrize("nx", [256, 2048])
+def test_staged_inputs_seed_like_direct_ones(nx):
+    """stage_inputs() + set_q() / set_phi() without an argument (niwqg_stage_q / niwqg_stage_phi: the upload runs ahead of
+    time on the copy stream) leave the model in exactly the state set_q(q) / set_phi(phi) do; staging twice in a row
+    (a second array queued while the first step runs) and stepping in between works; nothing staged -> error."""
+    import torch
+    from niwqg_b200 import InitialConditions as ic
+    a, b, U0, k0 = _pair(nx)
+    rng = np.random.RandomState(5)
+    q = ic.LambDipole(a, U=U0, R=2 * np.pi / k0) if nx <= 512 else 1e-5 * rng.randn(nx, nx)
+    phi = (1 + 1j) * 0.14 + 0.01 * (rng.randn(nx, nx) + 1j * rng.randn(nx, nx))
+    q_pin = torch.from_numpy(q.copy()).pin_memory()
+    phi_pin = torch.from_numpy(phi.copy()).pin_memory()
+    with pytest.raises(RuntimeError):
+        b.set_q()
+    for it in range(2):
+        a.set_q(q); a.set_phi(phi)
+        if it == 0:
+            b.stage_inputs(q=q_pin.numpy(), phi=phi_pin.numpy())
+        b.set_q(); b.set_phi()
+        b.stage_inputs(q=q_pin.numpy(), phi=phi_pin.numpy())     # next iteration's inputs, copied while the step runs
+        a._step_forward(); b._step_forward()
+        assert np.array_equal(a.q, b.q) and np.array_equal(a.phi, b.phi) and np.array_equal(a.qh, b.qh)
+        assert a.Ke == b.Ke and a.Kw == b.Kw
+    with pytest.raises(RuntimeError):
+        b.set_q(); b.set_q()
