@@ -84,7 +84,12 @@ struct FftArgs {
                       // half of every SM to the pass that runs concurrently on the other lane (slab overlap)
     int variant;      // tuning: bit 0 / bit 1 = column / row cluster passes use the decimation-in-time (pull) kernel;
                       // bit 2 = the push kernel uses plain remote stores + a cluster barrier instead of st.async
+    // row pass with a physical-product loader (k_fft_pass<..., LD>): further operands in the layout of `in`
+    const cd *in2, *in3;
+    double ld_scale;  // LD_WAVEPV: jscale of the Jacobian partner
 };
+// loaders: what a forward row pass forms from its operands while loading them (instead of a pointwise kernel + a re-read)
+enum { LD_NONE = 0, LD_WAVEPV };   // LD_WAVEPV: |phi|^2 + i jscale i J(phi*, phi) from in = phi, in2 = phix, in3 = phiy (k_phys_wavepv)
 
 // element n of line `line`: offset inside one member's array
 //   column pass: n-th row of local column `line`;  row pass: natural [line][n], or - on the exchange side of a slab
@@ -291,7 +296,7 @@ __device__ __forceinline__ void fft_prefetch(const FftArgs& a, int group, int c,
     }
 }
 
-template <int M, int W, int C, bool COL, bool NAT>
+template <int M, int W, int C, bool COL, bool NAT, int LD = LD_NONE>
 __global__ void __launch_bounds__(W * M / 16, Tile<M, W, C, COL>::MINB)
 k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
     using TL = Tile<M, W, C, COL>;
@@ -311,7 +316,31 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
     cd v[fftc::E];
     fft_prefetch<M, W, C, COL>(a, group, c, tid);
     bool tma_done = false;
-    if constexpr (COL && NAT && C == 1 && M >= 256) {
+    if constexpr (LD == LD_WAVEPV) {
+        // forward row pass of the wave-PV pair: the tile is FORMED from phi, phix, phiy while it is loaded
+        // (CoupledModel.py:75-90; same arithmetic as k_phys_wavepv), four points (12 loads) in flight per thread
+        static_assert(!COL && NAT && C == 1, "loader passes are one-tile row passes");
+        const size_t i0 = mbase + (size_t)group * W * N + (size_t)w * M + j;
+        const cd* __restrict__ p0 = (const cd*)a.in + i0;
+        const cd* __restrict__ p1 = a.in2 + i0;
+        const cd* __restrict__ p2 = a.in3 + i0;
+#pragma unroll
+        for (int b = 0; b < fftc::E; b += 4) {
+            cd x0[4], x1[4], x2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x0[i] = __ldg(p0 + (b + i) * TL::TPF); x1[i] = __ldg(p1 + (b + i) * TL::TPF); x2[i] = __ldg(p2 + (b + i) * TL::TPF);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double im = x1[i].x * x2[i].y - x1[i].y * x2[i].x;
+                v[b + i] = make_double2(x0[i].x * x0[i].x + x0[i].y * x0[i].y, a.ld_scale * (-2.0 * im));
+            }
+        }
+        for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+        tma_done = true;
+    }
+    if constexpr (LD == LD_NONE && COL && NAT && C == 1 && M >= 256) {
         if (a.tma_in & 1) {
             // the whole W x M tile by TMA: boxes of 256 rows x (W*16) bytes land densely ([row][W]) in the exchange buffer
             const unsigned bar = smem_u32(smtw + TL::TWLEN);
@@ -334,7 +363,7 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
             tma_done = true;
         }
     }
-    if constexpr (!COL && NAT && C == 1 && M * W == 4096) {
+    if constexpr (LD == LD_NONE && !COL && NAT && C == 1 && M * W == 4096) {
         if ((a.tma_in & 2) && a.pro != PRO_REAL_IN) {
             // row pass, one tile: the W lines of the group are one contiguous 64 KB block - ONE bulk copy into the
             // exchange buffer instead of 16 LDG.128 per thread (A/B against the register loads: profiles/r02_*)

@@ -171,6 +171,27 @@ static cudaError_t launch_split_colsub(const FftArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// forward row pass of the split path (2N lines of N/2) that forms its input with a loader (LD_*): in / in2 / in3 -> out
+template <int N, int LD>
+static cudaError_t launch_split_rows_loader(const FftArgs& a, cudaStream_t st) {
+    constexpr int Nh = N / 2, W = 4096 / Nh;
+    using TL = Tile<Nh, W, 1, false>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_fft_pass<Nh, W, 1, false, true, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev < 64) attr_set[dev] = true;
+    }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    FftArgs b = a;
+    b.tma_in = 0; b.pf_groups = 0;
+    k_fft_pass<Nh, W, 1, false, true, LD><<<dim3(a.nlines / W, 1, 1), TL::T, TL::SMEM, st>>>(b, tmap);
+    return cudaGetLastError();
+}
+
 template <int N, bool DIT>
 static cudaError_t launch_split_p(const SplitPArgs& a, cudaStream_t st) {
     k_split_p<N, DIT><<<dim3(N / 2 / 128, N / 16, 1), 256, 0, st>>>(a);

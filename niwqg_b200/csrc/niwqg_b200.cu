@@ -132,6 +132,7 @@ struct niwqg_handle {
     int row_bulk = 1;           // split path: row tiles fetched by one bulk copy (cp.async.bulk; NIWQG_ROW_BULK=0: 16 LDG.128 per thread)
     int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
                                 // NIWQG_FUSED=0 runs the stage as launches of its own
+    int row_loader = 1;         // split path: physical products formed by the forward row passes' loaders (NIWQG_ROW_LOADER=0: pointwise kernels)
     int hsym = 1;               // q-equation stage kernels update one element of every (K, -K) pair and store both (NIWQG_HSYM=0: every element)
     int fused_pf = 0;           // fused kernels prefetch the next unit's operands into L2 (NIWQG_FUSED_PF=1)
     int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
@@ -149,7 +150,7 @@ struct niwqg_handle {
     size_t prof_used = 0;
 };
 
-enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_FFT_P, PK_COUNT };
+enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_FFT_P, PK_FFT_ROWLD, PK_COUNT };
 
 static cudaEvent_t prof_event(niwqg_handle* h) {
     if (h->prof_used == h->prof_pool.size()) {
@@ -305,6 +306,29 @@ static int split_rows(niwqg_handle* h, const void* in, void* out, int pro, int e
     a.tma_in = h->row_bulk ? 2 : 0;
     a.pf_groups = 0;       // measured on 16384 lines of 4096: 0.362 ms without the L2 prefetch, 0.382 ms with it
     { PROF(PK_FFT_ROW); CK(launch_pass<false>(Nh, a, 1, h->stream)); }
+    h->launches++;
+    return 0;
+}
+// forward row pass that forms W = |phi|^2 + i jscale i J(phi*,phi) while loading phi, phix, phiy (replaces k_phys_wavepv
+// and the re-read of W; NIWQG_ROW_LOADER=0 keeps the pointwise kernel)
+static int split_rows_wavepv(niwqg_handle* h, cd* out) {
+    FftArgs a{};
+    fft_common_args(h, a);
+    const int Nh = h->N / 2;
+    a.in = h->phi; a.in2 = h->phix; a.in3 = h->phiy; a.ld_scale = h->jscale;
+    a.out = out; a.pro = PRO_NONE; a.epi = EPI_NONE; a.tw = h->tw_half;
+    a.nlines = 2 * h->N; a.pitch = Nh; a.mstride = (size_t)Nh * Nh; a.g = Grid{Nh, h->dk, Nh, Nh / 2, 0, 0};
+    a.conj_in = 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
+    cudaError_t e = cudaErrorInvalidValue;
+    {
+        PROF(PK_FFT_ROWLD);
+        switch (h->N) {
+            case 2048: e = launch_split_rows_loader<2048, LD_WAVEPV>(a, h->stream); break;
+            case 4096: e = launch_split_rows_loader<4096, LD_WAVEPV>(a, h->stream); break;
+            case 8192: e = launch_split_rows_loader<8192, LD_WAVEPV>(a, h->stream); break;
+        }
+    }
+    CK(e);
     h->launches++;
     return 0;
 }
@@ -824,10 +848,14 @@ static int step_family_fused_n(niwqg_handle* h) {
             if ((r = split_rows(h, h->phix, h->phix, PRO_NONE, EPI_NONE, sc, true))) return r;
             if ((r = split_colsub(h, h->T[0], h->phiy, false))) return r;
             if ((r = split_rows(h, h->phiy, h->phiy, PRO_NONE, EPI_NONE, sc, true))) return r;
-            { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
-            CK(cudaGetLastError());
-            h->launches++;
-            if ((r = split_rows(h, h->W, h->W, PRO_NONE, EPI_NONE, 1.0, false))) return r;
+            if (h->row_loader) {
+                if ((r = split_rows_wavepv(h, h->W))) return r;
+            } else {
+                { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
+                CK(cudaGetLastError());
+                h->launches++;
+                if ((r = split_rows(h, h->W, h->W, PRO_NONE, EPI_NONE, 1.0, false))) return r;
+            }
             if ((r = split_colsub(h, h->W, h->T[0], true))) return r;
         }
         // _invert(); _calc_rel_vorticity(); u, v
@@ -1219,6 +1247,7 @@ static int create_impl(niwqg_handle* h) {
         if (const char* f = getenv("NIWQG_FUSED")) h->fused = atoi(f);
         if (const char* f = getenv("NIWQG_ROW_BULK")) h->row_bulk = atoi(f);
         if (const char* f = getenv("NIWQG_FUSED_PF")) h->fused_pf = atoi(f);
+        if (const char* f = getenv("NIWQG_ROW_LOADER")) h->row_loader = atoi(f);
         if (const char* f = getenv("NIWQG_FUSED_GRID")) h->fused_grid = atoi(f);
         if (h->split) { h->deintM = N / 2; h->deintC = 2; }
     }

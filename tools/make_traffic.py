@@ -28,11 +28,16 @@ for (_, name), d in per.items():
 rows_n = sum(k["n"] for n, k in kinds.items() if n.startswith("k_fft_pass"))
 cols_n = sum(k["n"] for n, k in kinds.items() if n.startswith("k_fft_colsub"))
 n2d = max(rows_n, cols_n)
+# row passes with a loader (last template argument 1: k_fft_pass<M, W, 1, 0, 1, 1>) read three fields instead of one: they
+# count as one pass more (64 B per point instead of 32)
+n_ld = sum(k["n"] for n, k in kinds.items() if n.startswith("k_fft_pass") and n.rstrip(">").split(",")[-1].strip() == "1"
+           and len(n.split(",")) == 6)
 total = sum(k["bytes"] for k in kinds.values())
 model, nx, batch = WORKLOADS[workload]
 alg = 32.0 * nx * nx * batch
-rec = {"dram_bytes_per_pass": total / (2 * n2d), "algorithmic_bytes_per_pass": alg, "ratio": total / (2 * n2d) / alg,
-       "transforms_captured": n2d, "csrc_hash": csrc_hash(), "source": source,
+npass = 2 * n2d + n_ld
+rec = {"dram_bytes_per_pass": total / npass, "algorithmic_bytes_per_pass": alg, "ratio": total / npass / alg,
+       "transforms_captured": n2d, "loader_row_passes_captured": n_ld, "csrc_hash": csrc_hash(), "source": source,
        "kernels": {n: {"launches": k["n"], "dram_bytes_per_launch": k["bytes"] / k["n"], "avg_us": k["ns"] / k["n"] / 1e3}
                    for n, k in kinds.items()}}
 out = os.path.join(ROOT, "profiles", "traffic.json")
