@@ -1339,7 +1339,11 @@ static int create_impl(niwqg_handle* h) {
     h->lane_comm[0] = h->comm;
     // measured: 7% at 512^2, nothing at 2048^2, slightly negative at 8192^2 (the step is a chain of dependent kernels,
     // ~5 us each whatever launches them) -> small grids only
-    h->use_graphs = (h->nranks == 1) && N <= 1024 && !getenv("NIWQG_NO_GRAPH");
+    {
+        int maxn = 1024;      // larger grids: kernels of 0.4-2 ms, the launch gaps a graph removes are noise (A/B knob)
+        if (const char* e = getenv("NIWQG_GRAPH_MAXN")) maxn = atoi(e);
+        h->use_graphs = (h->nranks == 1) && N <= maxn && !getenv("NIWQG_NO_GRAPH");
+    }
     if (h->split) {
         for (int o = 0; o < 3; ++o) DA(h->T[o], fsz);
         std::vector<cd> tw;
