@@ -191,10 +191,10 @@ int niwqg_sync(niwqg_handle* h);
 /* CUDA-event timing on the handle's stream: elapsed ms of `nsteps` steps */
 int niwqg_time_steps(niwqg_handle* h, int nsteps, float* ms);
 /* per-kernel-kind CUDA-event timing on the handle's stream.  Reads the records accumulated since the
- * last call into ms_out[8] / count_out[8] (kinds: 0 FFT row pass, 1 FFT column pass, 2 physical-space
+ * last call into ms_out[9] / count_out[9] (kinds: 0 FFT row pass, 1 FFT column pass, 2 physical-space
  * pointwise, 3 spectral pointwise, 4 small reductions, 5 NCCL all-to-all / barriers of slab transforms, 6 stand-alone
- * radix stage of the split transforms, 7 forward row pass that forms its input from several physical fields while
- * loading them), clears them and switches recording on/off.
+ * radix stage of the split transforms, 7 / 8 forward row pass that forms its input from three / two physical fields
+ * while loading them), clears them and switches recording on/off.
  * ms_out/count_out may be NULL. */
 int niwqg_profile(niwqg_handle* h, int enable, double* ms_out, long long* count_out);
 /* number of kernel launches issued by this handle so far */

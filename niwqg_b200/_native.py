@@ -294,7 +294,7 @@ class Handle(object):
     def sync(self):
         self._ck(self.lib.niwqg_sync(self.h))
 
-    PROFILE_KINDS = ("fft_row", "fft_col", "phys", "spec", "small", "comm", "fft_p", "fft_row_ld")
+    PROFILE_KINDS = ("fft_row", "fft_col", "phys", "spec", "small", "comm", "fft_p", "fft_row_ld", "fft_row_ld2")
 
     def profile(self, enable):
         """Switch per-kernel-kind event timing on/off; returns {kind: (total_ms, launches)} recorded so far."""

@@ -89,7 +89,11 @@ struct FftArgs {
     double ld_scale;  // LD_WAVEPV: jscale of the Jacobian partner
 };
 // loaders: what a forward row pass forms from its operands while loading them (instead of a pointwise kernel + a re-read)
-enum { LD_NONE = 0, LD_WAVEPV };   // LD_WAVEPV: |phi|^2 + i jscale i J(phi*, phi) from in = phi, in2 = phix, in3 = phiy (k_phys_wavepv)
+enum {
+    LD_NONE = 0,
+    LD_WAVEPV,    // |phi|^2 + i jscale i J(phi*, phi) from in = phi, in2 = phix, in3 = phiy (k_phys_wavepv)
+    LD_UQVQ,      // u q + i v q from in = u + i v, in2 = q + i qw (the P1 product of k_phys_rhs, Kernel.py:479-483)
+};
 
 // element n of line `line`: offset inside one member's array
 //   column pass: n-th row of local column `line`;  row pass: natural [line][n], or - on the exchange side of a slab
@@ -336,6 +340,22 @@ k_fft_pass(FftArgs a, const __grid_constant__ CUtensorMap tmap) {
                 const double im = x1[i].x * x2[i].y - x1[i].y * x2[i].x;
                 v[b + i] = make_double2(x0[i].x * x0[i].x + x0[i].y * x0[i].y, a.ld_scale * (-2.0 * im));
             }
+        }
+        for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
+        tma_done = true;
+    }
+    if constexpr (LD == LD_UQVQ) {
+        static_assert(!COL && NAT && C == 1, "loader passes are one-tile row passes");
+        const size_t i0 = mbase + (size_t)group * W * N + (size_t)w * M + j;
+        const cd* __restrict__ p0 = (const cd*)a.in + i0;
+        const cd* __restrict__ p1 = a.in2 + i0;
+#pragma unroll
+        for (int b = 0; b < fftc::E; b += 8) {
+            cd x0[8], x1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { x0[i] = __ldg(p0 + (b + i) * TL::TPF); x1[i] = __ldg(p1 + (b + i) * TL::TPF); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[b + i] = make_double2(x0[i].x * x1[i].x, x0[i].y * x1[i].x);
         }
         for (int t = tid; t < TL::TWLEN; t += TL::T) smtw[t] = a.tw[t];
         tma_done = true;

@@ -20,6 +20,7 @@ enum {
     MF_SKIP_P2   = 1 << 7,   // [D] first half of a QL stage: P1 + sums only
     MF_SPEC_BUDGET = 1 << 8, // Coupled / UnCoupled: the stage budgets' lapphi terms are evaluated in spectral space
                              // (Parseval, see k_spec_stage), so lapphi / lap2phi are not transformed during a step
+    MF_P1_BY_LOADER = 1 << 9,   // k_phys_rhs does not store P1 = (uq, vq): P1's forward row pass forms it itself (LD_UQVQ)
 };
 
 // Grid (N, dk, local spectral columns, slab ownership) and the column maps grid_kx / grid_partner: common.cuh
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(NIWQG_PW_THREADS) k_phys_rhs(PhysArgs a) {
             Jadv = make_double2(w.x * px.x + w.y * py.x, w.x * px.y + w.y * py.y);
         }
         if (wr) {
-            if (!ybj && !(a.flags & MF_SKIP_P1)) a.P1[mb + i] = make_double2(u * q, v * q);
+            if (!ybj && !(a.flags & (MF_SKIP_P1 | MF_P1_BY_LOADER))) a.P1[mb + i] = make_double2(u * q, v * q);
             if (!(a.flags & MF_SKIP_P2))
                 a.P2[mb + i] = make_double2(-Jadv.x + 0.5 * phi.y * qpsi, -Jadv.y - 0.5 * phi.x * qpsi);
         }

@@ -132,7 +132,8 @@ struct niwqg_handle {
     int row_bulk = 1;           // split path: row tiles fetched by one bulk copy (cp.async.bulk; NIWQG_ROW_BULK=0: 16 LDG.128 per thread)
     int fused = 1;              // split path, Coupled / UnCoupled: spectral kernels fused with the radix stage (kernels_fused.cuh);
                                 // NIWQG_FUSED=0 runs the stage as launches of its own
-    int row_loader = 1;         // split path: physical products formed by the forward row passes' loaders (NIWQG_ROW_LOADER=0: pointwise kernels)
+    int row_loader = 3;         // split path: physical products formed by the forward row passes' loaders: bit 0 wave-PV pair,
+                                // bit 1 (uq, vq)  (NIWQG_ROW_LOADER=0: pointwise kernels)
     int hsym = 1;               // q-equation stage kernels update one element of every (K, -K) pair and store both (NIWQG_HSYM=0: every element)
     int fused_pf = 0;           // fused kernels prefetch the next unit's operands into L2 (NIWQG_FUSED_PF=1)
     int fused_grid = 296;       // persistent grid of the fused kernels: 2 CTAs per SM
@@ -150,7 +151,7 @@ struct niwqg_handle {
     size_t prof_used = 0;
 };
 
-enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_FFT_P, PK_FFT_ROWLD, PK_COUNT };
+enum { PK_FFT_ROW = 0, PK_FFT_COL, PK_PHYS, PK_SPEC, PK_SMALL, PK_COMM, PK_FFT_P, PK_FFT_ROWLD, PK_FFT_ROWLD2, PK_COUNT };
 
 static cudaEvent_t prof_event(niwqg_handle* h) {
     if (h->prof_used == h->prof_pool.size()) {
@@ -309,24 +310,29 @@ static int split_rows(niwqg_handle* h, const void* in, void* out, int pro, int e
     h->launches++;
     return 0;
 }
-// forward row pass that forms W = |phi|^2 + i jscale i J(phi*,phi) while loading phi, phix, phiy (replaces k_phys_wavepv
-// and the re-read of W; NIWQG_ROW_LOADER=0 keeps the pointwise kernel)
-static int split_rows_wavepv(niwqg_handle* h, cd* out) {
+// forward row pass that forms its input while loading the operands: LD_WAVEPV W = |phi|^2 + i jscale i J(phi*,phi) from phi,
+// phix, phiy (replaces k_phys_wavepv and the re-read of W), LD_UQVQ P1 = (uq, vq) from uv, qs (k_phys_rhs then skips the P1
+// store); NIWQG_ROW_LOADER=0 keeps the pointwise kernels
+static int split_rows_loader(niwqg_handle* h, int ld, cd* out) {
     FftArgs a{};
     fft_common_args(h, a);
     const int Nh = h->N / 2;
-    a.in = h->phi; a.in2 = h->phix; a.in3 = h->phiy; a.ld_scale = h->jscale;
+    if (ld == LD_WAVEPV) { a.in = h->phi; a.in2 = h->phix; a.in3 = h->phiy; a.ld_scale = h->jscale; }
+    else { a.in = h->uv; a.in2 = h->qs; a.in3 = nullptr; a.ld_scale = 1.0; }
     a.out = out; a.pro = PRO_NONE; a.epi = EPI_NONE; a.tw = h->tw_half;
     a.nlines = 2 * h->N; a.pitch = Nh; a.mstride = (size_t)Nh * Nh; a.g = Grid{Nh, h->dk, Nh, Nh / 2, 0, 0};
     a.conj_in = 0; a.conj_out = 0; a.scale = 1.0; a.scale_im = 1.0;
     cudaError_t e = cudaErrorInvalidValue;
     {
-        PROF(PK_FFT_ROWLD);
+        PROF(ld == LD_WAVEPV ? PK_FFT_ROWLD : PK_FFT_ROWLD2);
+#define NIWQG_LD_CASE(NN) case NN: e = (ld == LD_WAVEPV) ? launch_split_rows_loader<NN, LD_WAVEPV>(a, h->stream) \
+                                                          : launch_split_rows_loader<NN, LD_UQVQ>(a, h->stream); break;
         switch (h->N) {
-            case 2048: e = launch_split_rows_loader<2048, LD_WAVEPV>(a, h->stream); break;
-            case 4096: e = launch_split_rows_loader<4096, LD_WAVEPV>(a, h->stream); break;
-            case 8192: e = launch_split_rows_loader<8192, LD_WAVEPV>(a, h->stream); break;
+            NIWQG_LD_CASE(2048)
+            NIWQG_LD_CASE(4096)
+            NIWQG_LD_CASE(8192)
         }
+#undef NIWQG_LD_CASE
     }
     CK(e);
     h->launches++;
@@ -809,12 +815,13 @@ static int step_family_fused_n(niwqg_handle* h) {
     const int grid = h->fused_grid;
     int r;
     for (int st = 1; st <= 4; ++st) {
-        PhysArgs pa = phys_args(h, 0);
+        PhysArgs pa = phys_args(h, (h->row_loader & 2) ? MF_P1_BY_LOADER : 0);
         { PROF(PK_PHYS); k_phys_rhs<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(pa); }
         CK(cudaGetLastError());
         h->launches++;
         FIN(SD_COUNT, h->sumsD);
-        if ((r = split_rows(h, h->P1, h->P1, PRO_NONE, EPI_NONE, 1.0, false))) return r;
+        if (h->row_loader & 2) { if ((r = split_rows_loader(h, LD_UQVQ, h->P1))) return r; }   // P1 = (uq, vq) formed while loading uv, qs
+        else if ((r = split_rows(h, h->P1, h->P1, PRO_NONE, EPI_NONE, 1.0, false))) return r;
         if ((r = split_colsub(h, h->P1, h->T[0], true))) return r;
         if ((r = split_rows(h, h->P2, h->P2, PRO_NONE, EPI_NONE, 1.0, false))) return r;
         if ((r = split_colsub(h, h->P2, h->T[1], true))) return r;
@@ -848,8 +855,8 @@ static int step_family_fused_n(niwqg_handle* h) {
             if ((r = split_rows(h, h->phix, h->phix, PRO_NONE, EPI_NONE, sc, true))) return r;
             if ((r = split_colsub(h, h->T[0], h->phiy, false))) return r;
             if ((r = split_rows(h, h->phiy, h->phiy, PRO_NONE, EPI_NONE, sc, true))) return r;
-            if (h->row_loader) {
-                if ((r = split_rows_wavepv(h, h->W))) return r;
+            if (h->row_loader & 1) {
+                if ((r = split_rows_loader(h, LD_WAVEPV, h->W))) return r;
             } else {
                 { PROF(PK_PHYS); k_phys_wavepv<<<pw_grid(h), NIWQG_PW_THREADS, 0, h->stream>>>(h->phi, h->phix, h->phiy, h->W, h->npts, h->jscale); }
                 CK(cudaGetLastError());

@@ -30,14 +30,17 @@ cols_n = sum(k["n"] for n, k in kinds.items() if n.startswith("k_fft_colsub"))
 n2d = max(rows_n, cols_n)
 # row passes with a loader (last template argument 1: k_fft_pass<M, W, 1, 0, 1, 1>) read three fields instead of one: they
 # count as one pass more (64 B per point instead of 32)
-n_ld = sum(k["n"] for n, k in kinds.items() if n.startswith("k_fft_pass") and n.rstrip(">").split(",")[-1].strip() == "1"
-           and len(n.split(",")) == 6)
+def _ld(n):
+    parts = n.rstrip(">").split(",")
+    return int(parts[-1]) if n.startswith("k_fft_pass") and len(parts) == 6 else 0
+n_ld = sum(k["n"] for n, k in kinds.items() if _ld(n) == 1)       # three operands: +32 B per point
+n_ld2 = sum(k["n"] for n, k in kinds.items() if _ld(n) == 2)      # two operands: +16 B per point
 total = sum(k["bytes"] for k in kinds.values())
 model, nx, batch = WORKLOADS[workload]
 alg = 32.0 * nx * nx * batch
-npass = 2 * n2d + n_ld
+npass = 2 * n2d + n_ld + 0.5 * n_ld2
 rec = {"dram_bytes_per_pass": total / npass, "algorithmic_bytes_per_pass": alg, "ratio": total / npass / alg,
-       "transforms_captured": n2d, "loader_row_passes_captured": n_ld, "csrc_hash": csrc_hash(), "source": source,
+       "transforms_captured": n2d, "loader_row_passes_captured": n_ld + n_ld2, "csrc_hash": csrc_hash(), "source": source,
        "kernels": {n: {"launches": k["n"], "dram_bytes_per_launch": k["bytes"] / k["n"], "avg_us": k["ns"] / k["n"] / 1e3}
                    for n, k in kinds.items()}}
 out = os.path.join(ROOT, "profiles", "traffic.json")
