@@ -143,3 +143,26 @@ def test_params_struct_matches_header_in_native_and_in_integration_doc():
     exec(cls_src, ns)
     assert _ctypes_fields(ns["Params"]) == want
     assert C.sizeof(ns["Params"]) == C.sizeof(_native.Params)
+
+
+def test_traffic_record_matches_its_capture():
+    """profiles/traffic.json (what bench.py reports as roofline.traffic) is reproducible from the committed ncu capture:
+    DRAM bytes of all transform launches / algorithmic passes (a loader row pass counts 32 or 16 B per point more)."""
+    import csv, gzip, json, collections
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "traffic.json")))["coupled8192"]
+    rows = list(csv.reader(l for l in gzip.open(os.path.join(root, "profiles", "r02_fft_traffic.csv.gz"), "rt") if l.startswith('"')))
+    hdr = rows[0]
+    ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        per.setdefault((r[iid], r[ik].split("(")[0].replace("void ", "")), {})[r[im]] = float(r[iv].replace(",", ""))
+    total, npass = 0.0, 0.0
+    for (_, name), d in per.items():
+        total += d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]
+        parts = name.rstrip(">").split(",")
+        ld = int(parts[-1]) if name.startswith("k_fft_pass") and len(parts) == 6 else 0
+        npass += {0: 1.0, 1: 2.0, 2: 1.5}[ld]
+    assert len(per) == 2 * rec["transforms_captured"]
+    assert abs(total / npass - rec["dram_bytes_per_pass"]) <= 1e-6 * rec["dram_bytes_per_pass"]
+    assert 0.9 < rec["ratio"] <= 1.05
